@@ -1,0 +1,537 @@
+// agx_api.cu -- the C ABI of include/agxntt.h over the sm_100a kernels.  No torch types, no CPU fallback.
+#include "../../include/agxntt.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "agx_ntt_kernels.cuh"
+#include "agx_tables.h"
+
+using namespace agx;
+
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t e__ = (call);                  \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+namespace {
+
+constexpr int kSlots = 3;                          // host pipeline depth (H2D / kernel / D2H in flight)
+constexpr size_t kChunkBytes = 32u << 20;          // per-slot chunk of the host pipeline
+
+struct HostPipe {
+    cudaStream_t stream[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
+    uint32_t *d_a[kSlots] = {}, *d_b[kSlots] = {};
+    uint32_t *p_in[kSlots] = {}, *p_in2[kSlots] = {}, *p_out[kSlots] = {};   // pinned staging (pageable callers)
+    size_t cap = 0;                                // bytes per device / staging buffer
+    bool have_b = false, have_stage = false;
+};
+
+struct RefState {
+    bool have_in = false, have_fwd = false, have_out = false, busy = false;
+    uint32_t N = 0, frames = 0;
+    const uint64_t *in = nullptr, *in2 = nullptr, *mod = nullptr, *tw = nullptr, *pre = nullptr;
+    uint64_t *out = nullptr;
+    int32_t out_frames = 0;
+    uint64_t *d_in = nullptr, *d_in2 = nullptr, *d_out = nullptr, *d_tw = nullptr, *d_pre = nullptr;
+    size_t cap_data = 0, cap_tab = 0;
+    cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct agx_ctx {
+    int device = 0;
+    bool has_parms = false;
+    uint32_t n = 0, logn = 0, L = 0;
+    int le = 0;                                    // 0 = generic kernel
+    std::vector<uint32_t> q, psi;
+    std::vector<NaturalTables> nat_fwd, nat_inv;
+    uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural when le == 0)
+    LimbConst *d_lc = nullptr;
+    unsigned long long *d_sum = nullptr;
+    uint64_t launches = 0;
+    HostPipe pipe;
+    RefState ref;
+};
+
+namespace {
+
+int select_le(uint32_t logn) {
+    switch (logn) {
+        case 12: return 6;
+        case 11: return 6;
+        case 10: return 5;
+        default: return 0;
+    }
+}
+
+template <int LOGN, int LE>
+uint32_t kernel_pos(uint32_t k) {   // natural index k -> kernel-order index
+    constexpr int LT = LOGN - LE;
+    if (k < (1u << LE)) return k;
+    int s = 31 - __builtin_clz(k);
+    const uint32_t c = 1u << (s - LT), r = k - (1u << s);
+    return tw_pos<LOGN, LE>(s, r / c, r % c);
+}
+
+uint32_t kernel_pos_rt(uint32_t logn, int le, uint32_t k) {
+    if (le == 0) return k;
+    if (logn == 12) return kernel_pos<12, 6>(k);
+    if (logn == 11) return kernel_pos<11, 6>(k);
+    return kernel_pos<10, 5>(k);
+}
+
+int set_device(const agx_ctx *c) { CK(cudaSetDevice(c->device)); return AGX_OK; }
+
+int build_tables(agx_ctx *c) {
+    const uint32_t n = c->n, L = c->L;
+    std::vector<uint2> hf((size_t)L * n), hi((size_t)L * n);
+    std::vector<LimbConst> lc(L);
+    for (uint32_t l = 0; l < L; l++) {
+        const uint32_t q = c->q[l];
+        const uint32_t psi = minimal_psi(n, q);
+        if (!psi) return AGX_E_INVALID;
+        c->psi[l] = psi;
+        c->nat_fwd[l] = natural_tables(n, q, psi, false);
+        c->nat_inv[l] = natural_tables(n, q, psi, true);
+        const uint32_t ninv = (uint32_t)powmod_u64(n, q - 2, q);
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t pos = kernel_pos_rt(c->logn, c->le, k);
+            hf[(size_t)l * n + pos] = make_uint2(c->nat_fwd[l].w[k], c->nat_fwd[l].wp[k]);
+            uint32_t w = c->nat_inv[l].w[k];
+            if (k == 0) w = ninv;                                       // unused slot carries n^-1
+            if (k == 1 && c->le) w = (uint32_t)mulmod_u64(w, ninv, q);  // last GS stage folds n^-1 (two-pass kernels)
+            hi[(size_t)l * n + pos] = make_uint2(w, shoup_companion(w, q));
+        }
+        int k = 0;
+        while ((1ull << k) <= q) k++;                                   // bit length of q
+        LimbConst &x = lc[l];
+        x.q = q; x.twoq = 2 * q; x.negq = 0u - q; x.neg2q = 0u - 2 * q;
+        const uint64_t mu = (uint64_t)((((unsigned __int128)1) << (2 * k)) / q);
+        x.bar_mu = (uint32_t)(mu << (31 - k));
+        x.bar_sh = (uint32_t)(k - 1);
+        x.psi = psi; x.pad = 0;
+    }
+    CK(cudaMalloc(&c->d_tw_fwd, hf.size() * sizeof(uint2)));
+    CK(cudaMalloc(&c->d_tw_inv, hi.size() * sizeof(uint2)));
+    CK(cudaMalloc(&c->d_lc, lc.size() * sizeof(LimbConst)));
+    CK(cudaMalloc(&c->d_sum, sizeof(unsigned long long)));
+    CK(cudaMemcpy(c->d_tw_fwd, hf.data(), hf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_tw_inv, hi.data(), hi.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
+    return AGX_OK;
+}
+
+KParams kparams(const agx_ctx *c) { return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_lc, c->L}; }
+
+enum Op { OP_FWD, OP_INV, OP_MUL };
+
+template <int LOGN, int LE>
+int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
+    using G = Geo<LOGN, LE>;
+    const KParams p = kparams(c);
+    const dim3 grid((unsigned)T), block(G::TPP);
+    if (op == OP_FWD) ntt_fwd_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p);
+    else if (op == OP_INV) ntt_inv_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p);
+    else polymul_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
+    const size_t smem = (size_t)c->n * 4;
+    const unsigned threads = c->n / 2 < 256 ? (c->n / 2 < 32 ? 32 : c->n / 2) : 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+        CK(cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+        attr_done = true;
+    }
+    if (op == OP_FWD) {
+        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+        c->launches++;
+    } else if (op == OP_INV) {
+        ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
+        c->launches++;
+    } else {
+        // generic polymul: out <- a; fwd(out); fwd(tmp=b copy) needs scratch: use the pipe's device buffer? keep it
+        // simple and exact: three generic launches on caller buffers when out aliases neither input.
+        if (out == b || a == b) return AGX_E_UNSUPPORTED;
+        const size_t bytes = T * c->n * 4;
+        uint32_t *tmp = nullptr;
+        CK(cudaMallocAsync(&tmp, bytes, s));
+        if (out != a) CK(cudaMemcpyAsync(out, a, bytes, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(tmp, b, bytes, cudaMemcpyDeviceToDevice, s));
+        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(tmp, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+        const size_t total = T * c->n;
+        pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, tmp, c->d_lc, c->L, c->logn, total);
+        ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
+        c->launches += 4;
+        CK(cudaFreeAsync(tmp, s));
+    }
+    return (int)cudaGetLastError();
+}
+
+int launch(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t B, cudaStream_t s) {
+    const size_t T = B * c->L;
+    if (T == 0) return AGX_OK;
+    if (T > 0x7fffffffull) return AGX_E_INVALID;
+    switch (c->le ? c->logn : 0) {
+        case 12: return launch_fast<12, 6>(c, op, out, a, b, T, s);
+        case 11: return launch_fast<11, 6>(c, op, out, a, b, T, s);
+        case 10: return launch_fast<10, 5>(c, op, out, a, b, T, s);
+        default: return launch_generic(c, op, out, a, b, T, s);
+    }
+}
+
+int check_dev_call(agx_ctx *c, const void *p, size_t B) {
+    if (!c || !c->has_parms) return AGX_E_INVALID;
+    if (B && !p) return AGX_E_INVALID;
+    return set_device(c);
+}
+
+// ------------------------------------------------------------------------------------------- host pipeline
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
+    HostPipe &P = c->pipe;
+    if (!P.stream[0]) {
+        for (int i = 0; i < kSlots; i++) {
+            CK(cudaStreamCreateWithFlags(&P.stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
+        }
+        const size_t poly_bytes = (size_t)c->L * c->n * 4;
+        size_t polys = kChunkBytes / poly_bytes;
+        if (polys == 0) polys = 1;
+        P.cap = polys * poly_bytes;
+        for (int i = 0; i < kSlots; i++) CK(cudaMalloc(&P.d_a[i], P.cap));
+    }
+    if (need_b && !P.have_b) {
+        for (int i = 0; i < kSlots; i++) CK(cudaMalloc(&P.d_b[i], P.cap));
+        P.have_b = true;
+    }
+    if (need_stage && !P.have_stage) {
+        for (int i = 0; i < kSlots; i++) {
+            CK(cudaHostAlloc(&P.p_in[i], P.cap, cudaHostAllocDefault));
+            CK(cudaHostAlloc(&P.p_in2[i], P.cap, cudaHostAllocDefault));
+            CK(cudaHostAlloc(&P.p_out[i], P.cap, cudaHostAllocDefault));
+        }
+        P.have_stage = true;
+    }
+    return AGX_OK;
+}
+
+// Chunked pipeline: slot i%3 carries H2D -> kernel -> D2H on its own stream, so the copy engines and the SMs
+// overlap across slots (the GPU analogue of the reference's concurrently running loader/compute/drain kernels).
+int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32_t *h_out, size_t B) {
+    if (!c || !c->has_parms) return AGX_E_INVALID;
+    if (B == 0) return AGX_OK;
+    if (!h_a || !h_out || (op == OP_MUL && !h_b)) return AGX_E_INVALID;
+    int rc = set_device(c);
+    if (rc) return rc;
+    const bool pin_a = is_pinned(h_a), pin_b = op != OP_MUL || is_pinned(h_b), pin_o = is_pinned(h_out);
+    rc = pipe_prepare(c, op == OP_MUL, !(pin_a && pin_b && pin_o));
+    if (rc) return rc;
+    HostPipe &P = c->pipe;
+    const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
+    const size_t chunk_polys = P.cap / poly_bytes;
+    struct Pending { uint32_t *dst; size_t bytes; };
+    Pending pend[kSlots] = {};
+    size_t done = 0;
+    for (size_t i = 0; done < B; i++) {
+        const int sl = (int)(i % kSlots);
+        const size_t cnt = B - done < chunk_polys ? B - done : chunk_polys, bytes = cnt * poly_bytes;
+        const size_t off = done * poly_words;
+        if (i >= (size_t)kSlots) {                       // slot reuse: its previous chunk must have drained
+            CK(cudaEventSynchronize(P.done[sl]));
+            if (pend[sl].dst) { memcpy(pend[sl].dst, P.p_out[sl], pend[sl].bytes); pend[sl].dst = nullptr; }
+        }
+        const uint32_t *src_a = h_a + off;
+        if (!pin_a) { memcpy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
+        CK(cudaMemcpyAsync(P.d_a[sl], src_a, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
+        if (op == OP_MUL) {
+            const uint32_t *src_b = h_b + off;
+            if (!pin_b) { memcpy(P.p_in2[sl], src_b, bytes); src_b = P.p_in2[sl]; }
+            CK(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
+        }
+        rc = launch(c, op, P.d_a[sl], P.d_a[sl], P.d_b[sl], cnt, P.stream[sl]);
+        if (rc) return rc;
+        uint32_t *dst = h_out + off;
+        if (!pin_o) { pend[sl].dst = dst; pend[sl].bytes = bytes; dst = P.p_out[sl]; }
+        CK(cudaMemcpyAsync(dst, P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
+        CK(cudaEventRecord(P.done[sl], P.stream[sl]));
+        done += cnt;
+    }
+    for (int sl = 0; sl < kSlots; sl++) {
+        CK(cudaStreamSynchronize(P.stream[sl]));
+        if (pend[sl].dst) memcpy(pend[sl].dst, P.p_out[sl], pend[sl].bytes);
+    }
+    return AGX_OK;
+}
+
+void pipe_destroy(HostPipe &P) {
+    for (int i = 0; i < kSlots; i++) {
+        if (P.stream[i]) cudaStreamDestroy(P.stream[i]);
+        if (P.done[i]) cudaEventDestroy(P.done[i]);
+        cudaFree(P.d_a[i]); cudaFree(P.d_b[i]);
+        if (P.p_in[i]) cudaFreeHost(P.p_in[i]);
+        if (P.p_in2[i]) cudaFreeHost(P.p_in2[i]);
+        if (P.p_out[i]) cudaFreeHost(P.p_out[i]);
+    }
+    P = HostPipe{};
+}
+
+// ------------------------------------------------------------------------------- reference-shaped u64 pipeline
+
+int ref_flush(agx_ctx *c) {
+    RefState &R = c->ref;
+    if (!(R.have_in && R.have_fwd && R.have_out)) return AGX_OK;     // still waiting for the other calls
+    R.have_in = R.have_fwd = R.have_out = false;
+    if (R.out_frames < 0 || (uint32_t)R.out_frames != R.frames) return AGX_E_INVALID;
+    if (R.frames == 0) return AGX_OK;
+    int rc = set_device(c);
+    if (rc) return rc;
+    if (!R.stream) CK(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+    const size_t words = (size_t)R.N * R.frames;
+    if (words * 8 > R.cap_data) {
+        cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out);
+        R.d_in = R.d_in2 = R.d_out = nullptr; R.cap_data = 0;
+        CK(cudaMalloc(&R.d_in, words * 8)); CK(cudaMalloc(&R.d_in2, words * 8)); CK(cudaMalloc(&R.d_out, words * 8));
+        R.cap_data = words * 8;
+    }
+    if ((size_t)R.N * 8 > R.cap_tab) {
+        cudaFree(R.d_tw); cudaFree(R.d_pre);
+        R.d_tw = R.d_pre = nullptr; R.cap_tab = 0;
+        CK(cudaMalloc(&R.d_tw, (size_t)R.N * 8)); CK(cudaMalloc(&R.d_pre, (size_t)R.N * 8));
+        R.cap_tab = (size_t)R.N * 8;
+    }
+    const uint64_t modulus = R.mod[0];
+    CK(cudaMemcpyAsync(R.d_in, R.in, words * 8, cudaMemcpyHostToDevice, R.stream));
+    if (R.in2 == R.in) CK(cudaMemcpyAsync(R.d_in2, R.d_in, words * 8, cudaMemcpyDeviceToDevice, R.stream));
+    else CK(cudaMemcpyAsync(R.d_in2, R.in2, words * 8, cudaMemcpyHostToDevice, R.stream));
+    CK(cudaMemcpyAsync(R.d_tw, R.tw, (size_t)R.N * 8, cudaMemcpyHostToDevice, R.stream));
+    CK(cudaMemcpyAsync(R.d_pre, R.pre, (size_t)R.N * 8, cudaMemcpyHostToDevice, R.stream));
+    uint32_t logn = 0;
+    while ((1u << logn) < R.N) logn++;
+    const size_t smem = (size_t)R.N * 8;
+    const int use_smem = smem <= (128u << 10);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+        attr_done = true;
+    }
+    const unsigned threads = R.N / 2 < 1024 ? (R.N / 2 < 32 ? 32 : R.N / 2) : 1024;
+    ref_fwd_u64_kernel<<<R.frames, threads, use_smem ? smem : 0, R.stream>>>(R.d_in, R.d_in2, R.d_out, R.d_tw, R.d_pre,
+                                                                           modulus, logn, use_smem);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(R.out, R.d_out, words * 8, cudaMemcpyDeviceToHost, R.stream));
+    R.busy = true;
+    return AGX_OK;
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+
+extern "C" {
+
+int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
+    if (!out) return AGX_E_INVALID;
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    CK(cudaFree(0));
+    agx_ctx *c = new (std::nothrow) agx_ctx();
+    if (!c) return AGX_E_NOMEM;
+    c->device = device;
+    if (parms) {
+        if (!parms->q || parms->nlimbs == 0 || parms->nlimbs > 64 || parms->logn < 3 || parms->logn > 15 ||
+            parms->n != (1u << parms->logn)) { delete c; return AGX_E_INVALID; }
+        c->has_parms = true;
+        c->n = parms->n; c->logn = parms->logn; c->L = parms->nlimbs;
+        c->le = select_le(c->logn);
+        c->q.assign(parms->q, parms->q + parms->nlimbs);
+        c->psi.resize(c->L); c->nat_fwd.resize(c->L); c->nat_inv.resize(c->L);
+        const int rc = build_tables(c);
+        if (rc) { agx_destroy(c); return rc; }
+    }
+    *out = c;
+    return AGX_OK;
+}
+
+int agx_destroy(agx_ctx *c) {
+    if (!c) return AGX_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    pipe_destroy(c->pipe);
+    RefState &R = c->ref;
+    cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out); cudaFree(R.d_tw); cudaFree(R.d_pre);
+    if (R.stream) cudaStreamDestroy(R.stream);
+    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_lc); cudaFree(c->d_sum);
+    delete c;
+    return AGX_OK;
+}
+
+int agx_get_psi(const agx_ctx *c, uint32_t limb, uint32_t *psi) {
+    if (!c || !c->has_parms || limb >= c->L || !psi) return AGX_E_INVALID;
+    *psi = c->psi[limb];
+    return AGX_OK;
+}
+
+int agx_get_tables(const agx_ctx *c, uint32_t limb, int inverse, uint32_t *roots, uint32_t *precons) {
+    if (!c || !c->has_parms || limb >= c->L || !roots || !precons) return AGX_E_INVALID;
+    const NaturalTables &t = inverse ? c->nat_inv[limb] : c->nat_fwd[limb];
+    memcpy(roots, t.w.data(), (size_t)c->n * 4);
+    memcpy(precons, t.wp.data(), (size_t)c->n * 4);
+    return AGX_OK;
+}
+
+int agx_ntt_fwd(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
+    int rc = check_dev_call(c, d, B);
+    return rc ? rc : launch(c, OP_FWD, d, d, nullptr, B, (cudaStream_t)stream);
+}
+
+int agx_ntt_inv(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
+    int rc = check_dev_call(c, d, B);
+    return rc ? rc : launch(c, OP_INV, d, d, nullptr, B, (cudaStream_t)stream);
+}
+
+int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db, size_t B, void *stream) {
+    int rc = check_dev_call(c, dc, B);
+    if (rc) return rc;
+    if (B && (!da || !db)) return AGX_E_INVALID;
+    return launch(c, OP_MUL, dc, da, db, B, (cudaStream_t)stream);
+}
+
+int agx_ntt_fwd_host(agx_ctx *c, const uint32_t *h_in, uint32_t *h_out, size_t B) {
+    return run_host(c, OP_FWD, h_in, nullptr, h_out, B);
+}
+int agx_ntt_inv_host(agx_ctx *c, const uint32_t *h_in, uint32_t *h_out, size_t B) {
+    return run_host(c, OP_INV, h_in, nullptr, h_out, B);
+}
+int agx_polymul_host(agx_ctx *c, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b, size_t B) {
+    return run_host(c, OP_MUL, h_a, h_b, h_c, B);
+}
+
+int agx_host_alloc(void **p, size_t bytes) {
+    if (!p) return AGX_E_INVALID;
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return AGX_OK;
+}
+int agx_host_free(void *p) {
+    CK(cudaFreeHost(p));
+    return AGX_OK;
+}
+
+int agx_fill_synthetic(agx_ctx *c, uint32_t *d, size_t B, uint64_t seed, size_t first_poly, void *stream) {
+    int rc = check_dev_call(c, d, B);
+    if (rc || B == 0) return rc;
+    const size_t total = B * c->L * c->n;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fill_synthetic_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d, total, c->logn, c->L, c->d_lc, seed, (uint64_t)first_poly * c->L * c->n);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+int agx_checksum(agx_ctx *c, const uint32_t *d, size_t count, size_t first_index, uint64_t *h_sum, void *stream) {
+    if (!c || !c->has_parms || !h_sum || (count && !d)) return AGX_E_INVALID;
+    int rc = set_device(c);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), s));
+    if (count) {
+        size_t blocks = (count + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        checksum_kernel<<<(unsigned)blocks, 256, 0, s>>>(d, count, first_index, c->d_sum);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, c->d_sum, sizeof v, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *h_sum = v;
+    return AGX_OK;
+}
+
+int agx_ref_input(agx_ctx *c, uint32_t N, const uint64_t *in, const uint64_t *in2, const uint64_t *modulus,
+                  const uint64_t *twiddles, const uint64_t *precon_twiddles, uint32_t numFrames) {
+    if (!c || !in || !in2 || !modulus || !twiddles || !precon_twiddles) return AGX_E_INVALID;
+    if (N < 4 || N > 32768 || (N & (N - 1))) return AGX_E_INVALID;
+    RefState &R = c->ref;
+    if (R.have_in || R.busy) return AGX_E_STATE;
+    R.N = N; R.frames = numFrames; R.in = in; R.in2 = in2; R.mod = modulus; R.tw = twiddles; R.pre = precon_twiddles;
+    R.have_in = true;
+    return ref_flush(c);
+}
+
+int agx_ref_fwd(agx_ctx *c, uint32_t compute_unit_id) {
+    if (!c) return AGX_E_INVALID;
+    if (compute_unit_id != 0) return AGX_E_UNSUPPORTED;   // the reference instantiates only <0> (ntt.cpp:648)
+    if (c->ref.have_fwd || c->ref.busy) return AGX_E_STATE;
+    c->ref.have_fwd = true;
+    return ref_flush(c);
+}
+
+int agx_ref_output(agx_ctx *c, uint64_t *out, int32_t numFrames) {
+    if (!c || !out) return AGX_E_INVALID;
+    if (c->ref.have_out || c->ref.busy) return AGX_E_STATE;
+    c->ref.out = out; c->ref.out_frames = numFrames; c->ref.have_out = true;
+    return ref_flush(c);
+}
+
+int agx_wait(agx_ctx *c) {
+    if (!c) return AGX_E_INVALID;
+    RefState &R = c->ref;
+    if (R.have_in || R.have_fwd || R.have_out) {
+        // a partial round can never complete (the reference would hang on its pipes): report and reset
+        R.have_in = R.have_fwd = R.have_out = false;
+        return AGX_E_STATE;
+    }
+    if (R.busy) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(R.stream));
+        R.busy = false;
+    }
+    return AGX_OK;
+}
+
+const char *agx_error_string(int code) {
+    switch (code) {
+        case AGX_OK: return "ok";
+        case AGX_E_INVALID: return "invalid argument";
+        case AGX_E_UNSUPPORTED: return "unsupported request";
+        case AGX_E_NOMEM: return "host allocation failed";
+        case AGX_E_STATE: return "reference-shaped calls out of protocol";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int agx_launch_count(const agx_ctx *c, uint64_t *count) {
+    if (!c || !count) return AGX_E_INVALID;
+    *count = c->launches;
+    return AGX_OK;
+}
+
+int agx_variant(const agx_ctx *c, char *buf, size_t buflen) {
+    if (!c || !buf || !buflen) return AGX_E_INVALID;
+    if (!c->has_parms) snprintf(buf, buflen, "ref_u64");
+    else if (c->le) snprintf(buf, buflen, "ntt2p<%u,%d>", c->logn, c->le);
+    else snprintf(buf, buflen, "generic");
+    return AGX_OK;
+}
+
+}  // extern "C"

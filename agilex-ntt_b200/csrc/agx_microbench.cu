@@ -1,0 +1,115 @@
+// agx_microbench.cu -- integer-pipe microbenchmarks that turn the "integer roofline" of the NTT butterfly into a
+// MEASURED number on the B200 in front of us ("the 64/clk figure must be
+// microbenchmarked on the box first").  Stand-alone binary: prints one JSON object per line.
+//
+// Each test runs one CTA of 1024 threads per SM (8 warps per scheduler), every thread executing a long unrolled
+// stream of the instruction under test on 8 independent register chains; cycles are SM clock64() deltas, so the
+// result is lane-operations per clock per SM, independent of DVFS.
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "agx_arith.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("{\"error\": \"%s at %s:%d\"}\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+constexpr int CH = 8;        // independent chains per thread
+constexpr int UN = 16;       // unrolled repetitions of the chain set per loop iteration
+constexpr int ITERS = 256;
+
+enum Test { T_IMAD, T_IMADHI, T_IMADWIDE, T_VIADDMNMX, T_IADD3, T_LOP3, T_MIX_IMAD_IADD3, T_BFLY_CT, T_BFLY_GS, T_SHFL, T_COUNT };
+static const char *kNames[] = {"imad_lo", "imad_hi", "imad_wide", "viaddmnmx_u32", "iadd3", "lop3", "mix_imad+iadd3",
+                               "ct_butterfly", "gs_butterfly", "shfl_xor"};
+// lane-instructions issued per inner step per chain (for instr/clk) and "units" (butterflies) per step
+static const int kInstrPerStep[] = {1, 1, 1, 1, 1, 1, 2, 6, 6, 1};
+
+template <int TEST>
+__global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long *cycles, uint32_t seed, agx::LimbConst lc) {
+    uint32_t a[CH], b[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) { a[i] = seed + threadIdx.x * 977u + i * 131u; b[i] = (seed ^ 0x9e3779b9u) + i * 7919u + threadIdx.x; }
+    const uint2 w = make_uint2(seed | 1u, seed * 3u + 5u);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                if (TEST == T_IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(w.x));
+                else if (TEST == T_IMADHI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
+                else if (TEST == T_IMADWIDE) {
+                    unsigned long long r;
+                    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a[i]), "r"(b[i]));
+                    a[i] = (uint32_t)r; b[i] ^= (uint32_t)(r >> 32);
+                } else if (TEST == T_VIADDMNMX) a[i] = __viaddmin_u32(a[i], lc.neg2q, b[i]);
+                else if (TEST == T_IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
+                else if (TEST == T_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(w.y));
+                else if (TEST == T_MIX_IMAD_IADD3) {
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(w.x), "r"(w.y));
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(w.x));
+                } else if (TEST == T_BFLY_CT) agx::ct_bfly(a[i], b[i], w, lc);
+                else if (TEST == T_BFLY_GS) agx::gs_bfly(a[i], b[i], w, lc);
+                else if (TEST == T_SHFL) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1 + (i & 15));
+            }
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) acc ^= a[i] ^ b[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int TEST>
+int run(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cudaStream_t s) {
+    bench_kernel<TEST><<<sms, 1024, 0, s>>>(d_out, d_cyc, 12345u, lc);   // warm-up
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+    bench_kernel<TEST><<<sms, 1024, 0, s>>>(d_out, d_cyc, 12345u, lc);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> cyc(sms);
+    CK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    std::sort(cyc.begin(), cyc.end());
+    const double med = (double)cyc[sms / 2];
+    const double steps = (double)ITERS * UN * CH * 1024.0;          // per SM
+    const double lane_instr = steps * kInstrPerStep[TEST];
+    printf("{\"test\": \"%s\", \"lane_instr_per_clk_per_sm\": %.2f, \"units_per_clk_per_sm\": %.3f, \"median_cycles\": %.0f, "
+           "\"event_ms\": %.4f, \"implied_sm_mhz\": %.0f}\n",
+           kNames[TEST], lane_instr / med, steps / med, med, ms, med / (ms * 1e3));
+    return 0;
+}
+
+int main() {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\"}\n", prop.name, sms, prop.major, prop.minor);
+    uint32_t *d_out; long long *d_cyc;
+    CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * 1024));
+    CK(cudaMalloc(&d_cyc, sizeof(long long) * sms));
+    const uint32_t q = 1053818881u;
+    agx::LimbConst lc{q, 2 * q, 0u - q, 0u - 2 * q, 0, 29, 0, 0};
+    cudaStream_t s;
+    CK(cudaStreamCreate(&s));
+    if (run<T_IMAD>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_IMADHI>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_IMADWIDE>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_VIADDMNMX>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_IADD3>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_LOP3>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_MIX_IMAD_IADD3>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_BFLY_CT>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_BFLY_GS>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run<T_SHFL>(sms, d_out, d_cyc, lc, s)) return 1;
+    return 0;
+}

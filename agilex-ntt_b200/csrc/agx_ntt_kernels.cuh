@@ -1,0 +1,445 @@
+// agx_ntt_kernels.cuh -- register-resident two-pass negacyclic NTT kernels for sm_100a.
+//
+// Replaces the reference's loader + compute + drain single_tasks (ntt_input_kernel ntt.cpp:508-607,
+// fwd_ntt_kernel ntt.cpp:86-506, ntt_output_kernel ntt.cpp:610-640) with ONE kernel per direction: a CTA of
+// TPP = n/E threads owns one polynomial (one (batch, limb) row of the [B][L][n] array), each thread keeps
+// E = 2^LE coefficients in registers and the log2(n) butterfly stages run as two register-resident passes with
+// a single shared-memory transpose between them:
+//
+//   forward  pass A: thread t holds x[t + TPP*k]   -> stages 0..LE-1     (twiddles identical for all threads)
+//            transpose through XOR-swizzled smem (STS.32 columns -> LDS.128 rows, both conflict-free)
+//            pass B: thread T holds x[E*T .. E*T+E) -> stages LE..logn-1 (per-thread twiddles, coalesced 16-B loads
+//                                                      from a table stored in kernel order)
+//            final reduction to [0,q), staged through smem, written back with coalesced 16-B stores.
+//   inverse  is the mirror image (Gentleman-Sande), n^-1 folded into the last stage's twiddles.
+//   polymul  runs forward(a), parks it in smem, forward(b), pointwise Barrett, inverse -- one launch.
+//
+// The FPGA's X/X2/Xm double-buffer and reorder muxes (ntt.cpp:90-98, 160-289, 397-496) exist to dodge BRAM port
+// conflicts and have no arithmetic effect; they have no counterpart here.
+//
+// Twiddle table (per limb, per direction) `tw[n]` of (w, w') pairs:
+//   entries [1, E)      : natural order, entry k = psi^bitrev(k)  (ntt.cpp:298-300 indexing, roots[m + i])
+//   entries [2^s, 2^s+1): for stages s >= LE the 2^s entries of the stage are permuted so that thread T's
+//                         c = 2^(s-LT) twiddles are reached by coalesced loads:
+//                         natural 2^s + T*c + kk  ->  2^s + ((kk>>1)*TPP + T)*2 + (kk&1)   (c >= 2)
+//   inverse table: entry 0 = (n^-1, .), entry 1 = (psi^-bitrev(1) * n^-1, .)
+#pragma once
+#include "agx_arith.cuh"
+
+namespace agx {
+
+struct KParams {
+    const uint2 *tw_fwd;     // [L][n] kernel order
+    const uint2 *tw_inv;     // [L][n] kernel order
+    const LimbConst *lc;     // [L]
+    uint32_t L;
+};
+
+template <int LOGN, int LE>
+struct Geo {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int E = 1 << LE;            // coefficients per thread
+    static constexpr int LT = LOGN - LE;
+    static constexpr int TPP = 1 << LT;          // threads per polynomial
+    static constexpr int CPR = E / 4;            // 16-byte chunks per smem row
+    static constexpr int SW = (CPR < 8 ? CPR : 8) - 1;
+    static constexpr int SMEM_BYTES = N * 4;
+    static_assert(LT >= 5 && LT <= LE, "need 32 <= TPP <= E");
+};
+
+// kernel-order position of the twiddle for (stage s >= LE, thread T, local index kk)
+template <int LOGN, int LE>
+__host__ __device__ constexpr uint32_t tw_pos(int s, uint32_t T, uint32_t kk) {
+    constexpr int LT = LOGN - LE;
+    constexpr uint32_t TPP = 1u << LT;
+    const uint32_t c = 1u << (s - LT);
+    return c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * TPP + T) * 2 + (kk & 1);
+}
+
+template <int TPP>
+__device__ __forceinline__ void poly_sync() {
+    if constexpr (TPP == 32) __syncwarp(); else __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------- smem transposes
+
+// element e = tid + TPP*k lives at row e>>LE, column e&(E-1); 16-byte chunk index XOR-swizzled with row&SW.
+template <int LOGN, int LE>
+__device__ __forceinline__ uint32_t col_phys(uint32_t tid, int k) {
+    using G = Geo<LOGN, LE>;
+    const int ebase = G::TPP * k;
+    const int row = ebase >> LE;
+    const int colbase = ebase & (G::E - 1);
+    return row * G::E + ((colbase + tid) ^ ((row & G::SW) << 2));
+}
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void sts_columns(uint32_t *sw, const uint32_t (&x)[1 << LE], uint32_t tid) {
+#pragma unroll
+    for (int k = 0; k < (1 << LE); k++) sw[col_phys<LOGN, LE>(tid, k)] = x[k];
+}
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void lds_columns(const uint32_t *sw, uint32_t (&x)[1 << LE], uint32_t tid) {
+#pragma unroll
+    for (int k = 0; k < (1 << LE); k++) x[k] = sw[col_phys<LOGN, LE>(tid, k)];
+}
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void lds_row(const uint4 *sm, uint32_t (&x)[1 << LE], uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+#pragma unroll
+    for (int c = 0; c < G::CPR; c++) {
+        const uint4 v = sm[tid * G::CPR + (c ^ (tid & G::SW))];
+        x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+    }
+}
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void sts_row(uint4 *sm, const uint32_t (&x)[1 << LE], uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+#pragma unroll
+    for (int c = 0; c < G::CPR; c++)
+        sm[tid * G::CPR + (c ^ (tid & G::SW))] = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+
+// coalesced 16-byte copies between the swizzled smem image and the polynomial's row in global memory
+template <int LOGN, int LE>
+__device__ __forceinline__ void smem_to_global(const uint4 *sm, uint32_t *g, uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+    uint4 *g4 = reinterpret_cast<uint4 *>(g);
+#pragma unroll
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) {
+        const uint32_t idx = i * G::TPP + tid, row = idx / G::CPR, c = idx % G::CPR;
+        __stcs(g4 + idx, sm[row * G::CPR + (c ^ (row & G::SW))]);
+    }
+}
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+    uint4 v[G::N / 4 / G::TPP];
+#pragma unroll
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) v[i] = __ldcs(g4 + i * G::TPP + tid);
+#pragma unroll
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) {
+        const uint32_t idx = i * G::TPP + tid, row = idx / G::CPR, c = idx % G::CPR;
+        sm[row * G::CPR + (c ^ (row & G::SW))] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- the passes
+
+// forward pass A: stages 0..LE-1 on x[k] = elem[tid + TPP*k]; twiddle index 2^s + (k >> (LE-s)) (uniform)
+template <int LE>
+__device__ __forceinline__ void fwd_pass_a(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, const LimbConst &c) {
+#pragma unroll
+    for (int s = 0; s < LE; s++) {
+        const int half = (1 << LE) >> (s + 1);
+#pragma unroll
+        for (int g = 0; g < (1 << s); g++) {
+            const uint2 w = __ldg(tw + (1 << s) + g);
+#pragma unroll
+            for (int j = 0; j < half; j++) ct_bfly(x[g * 2 * half + j], x[g * 2 * half + j + half], w, c);
+        }
+    }
+}
+
+// twiddles of (stage s, thread T): c = 2^(s-LT) pairs, fetched as coalesced 16-byte loads
+template <int LOGN, int LE, int S>
+__device__ __forceinline__ void load_stage_tw(uint2 (&w)[1 << (S - (LOGN - LE))], const uint2 *__restrict__ tw,
+                                              uint32_t T) {
+    constexpr int LT = LOGN - LE, C = 1 << (S - LT), TPP = 1 << LT;
+    if constexpr (C == 1) {
+        w[0] = __ldg(tw + (1 << S) + T);
+    } else {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(tw + (1 << S));
+#pragma unroll
+        for (int h = 0; h < C / 2; h++) {
+            const uint4 v = __ldg(t4 + h * TPP + T);
+            w[2 * h] = make_uint2(v.x, v.y);
+            w[2 * h + 1] = make_uint2(v.z, v.w);
+        }
+    }
+}
+
+template <int LOGN, int LE, int S>
+__device__ __forceinline__ void fwd_stage_b(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, uint32_t T,
+                                            const LimbConst &c) {
+    constexpr int LT = LOGN - LE, C = 1 << (S - LT), half = 1 << (LOGN - 1 - S);
+    uint2 w[C];
+    load_stage_tw<LOGN, LE, S>(w, tw, T);
+#pragma unroll
+    for (int kk = 0; kk < C; kk++)
+#pragma unroll
+        for (int j = 0; j < half; j++) ct_bfly(x[kk * 2 * half + j], x[kk * 2 * half + j + half], w[kk], c);
+    if constexpr (S + 1 < LOGN) fwd_stage_b<LOGN, LE, S + 1>(x, tw, T, c);
+}
+
+template <int LOGN, int LE, int S>
+__device__ __forceinline__ void inv_stage_b(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, uint32_t T,
+                                            const LimbConst &c) {
+    constexpr int LT = LOGN - LE, C = 1 << (S - LT), half = 1 << (LOGN - 1 - S);
+    uint2 w[C];
+    load_stage_tw<LOGN, LE, S>(w, tw, T);
+#pragma unroll
+    for (int kk = 0; kk < C; kk++)
+#pragma unroll
+        for (int j = 0; j < half; j++) gs_bfly(x[kk * 2 * half + j], x[kk * 2 * half + j + half], w[kk], c);
+    if constexpr (S > LE) inv_stage_b<LOGN, LE, S - 1>(x, tw, T, c);
+}
+
+// inverse pass A': stages LE-1 .. 1 then stage 0 with n^-1 folded (tw[0] = n^-1, tw[1] = iroot1 * n^-1)
+template <int LE>
+__device__ __forceinline__ void inv_pass_a(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, const LimbConst &c) {
+#pragma unroll
+    for (int s = LE - 1; s >= 1; s--) {
+        const int half = (1 << LE) >> (s + 1);
+#pragma unroll
+        for (int g = 0; g < (1 << s); g++) {
+            const uint2 w = __ldg(tw + (1 << s) + g);
+#pragma unroll
+            for (int j = 0; j < half; j++) gs_bfly(x[g * 2 * half + j], x[g * 2 * half + j + half], w, c);
+        }
+    }
+    const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1);
+#pragma unroll
+    for (int j = 0; j < (1 << LE) / 2; j++) gs_bfly_last(x[j], x[j + (1 << LE) / 2], wn, w1n, c);
+}
+
+// ---- whole-polynomial cores shared by the three kernels -----------------------------------------------------
+
+// global (natural order) -> registers as rows: x[j] = NTT(poly)[E*tid + j], values in [0,4q)
+template <int LOGN, int LE>
+__device__ __forceinline__ void fwd_core(uint32_t (&x)[1 << LE], const uint32_t *__restrict__ g, uint4 *sm,
+                                         const uint2 *__restrict__ tw, const LimbConst &c, uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+#pragma unroll
+    for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
+    fwd_pass_a<LE>(x, tw, c);
+    sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
+    poly_sync<G::TPP>();
+    lds_row<LOGN, LE>(sm, x, tid);
+    fwd_stage_b<LOGN, LE, LE>(x, tw, tid, c);
+}
+
+// registers as rows (values < 2q) -> global natural order, fully reduced
+template <int LOGN, int LE>
+__device__ __forceinline__ void inv_core(uint32_t (&x)[1 << LE], uint32_t *__restrict__ g, uint4 *sm,
+                                         const uint2 *__restrict__ tw, const LimbConst &c, uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+    inv_stage_b<LOGN, LE, LOGN - 1>(x, tw, tid, c);
+    sts_row<LOGN, LE>(sm, x, tid);
+    poly_sync<G::TPP>();
+    lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
+    inv_pass_a<LE>(x, tw, c);
+#pragma unroll
+    for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
+}
+
+// ------------------------------------------------------------------------------------------------- the kernels
+
+#ifndef AGX_MINB
+#define AGX_MINB(LOGN, LE) ((1 << (LE)) >= 64 ? (512 >> ((LOGN) - (LE))) : (768 >> ((LOGN) - (LE))))
+#endif
+
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+ntt_fwd_kernel(uint32_t *__restrict__ data, KParams p) {
+    using G = Geo<LOGN, LE>;
+    __shared__ uint4 sm[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
+    uint32_t *g = data + (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+    fwd_core<LOGN, LE>(x, g, sm, tw, c, tid);
+#pragma unroll
+    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+    sts_row<LOGN, LE>(sm, x, tid);       // own row only: no barrier needed before
+    poly_sync<G::TPP>();
+    smem_to_global<LOGN, LE>(sm, g, tid);
+}
+
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+ntt_inv_kernel(uint32_t *__restrict__ data, KParams p) {
+    using G = Geo<LOGN, LE>;
+    __shared__ uint4 sm[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *tw = p.tw_inv + (size_t)limb * G::N;
+    uint32_t *g = data + (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+    global_to_smem<LOGN, LE>(sm, g, tid);
+    poly_sync<G::TPP>();
+    lds_row<LOGN, LE>(sm, x, tid);
+    inv_core<LOGN, LE>(x, g, sm, tw, c, tid);
+}
+
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+polymul_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+               KParams p) {
+    using G = Geo<LOGN, LE>;
+    __shared__ uint4 sm[G::N / 4];
+    __shared__ uint4 park[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *twf = p.tw_fwd + (size_t)limb * G::N;
+    const uint2 *twi = p.tw_inv + (size_t)limb * G::N;
+    const size_t off = (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+    fwd_core<LOGN, LE>(x, a + off, sm, twf, c, tid);
+#pragma unroll
+    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+    sts_row<LOGN, LE>(park, x, tid);     // NTT(a), own row, read back by the same thread only
+    poly_sync<G::TPP>();                 // everyone is done reading `sm` rows before b's columns overwrite them
+    fwd_core<LOGN, LE>(x, b + off, sm, twf, c, tid);
+#pragma unroll
+    for (int cc = 0; cc < G::CPR; cc++) {
+        const uint4 av = park[tid * G::CPR + (cc ^ (tid & G::SW))];
+        x[4 * cc + 0] = csub(barrett_mul_lazy(av.x, reduce4q(x[4 * cc + 0], c), c), c.neg2q);
+        x[4 * cc + 1] = csub(barrett_mul_lazy(av.y, reduce4q(x[4 * cc + 1], c), c), c.neg2q);
+        x[4 * cc + 2] = csub(barrett_mul_lazy(av.z, reduce4q(x[4 * cc + 2], c), c), c.neg2q);
+        x[4 * cc + 3] = csub(barrett_mul_lazy(av.w, reduce4q(x[4 * cc + 3], c), c), c.neg2q);
+    }
+    inv_core<LOGN, LE>(x, out + off, sm, twi, c, tid);
+}
+
+// ---------------------------------------------------------------------------------- generic (any n) u32 kernels
+// One CTA per polynomial, whole polynomial in dynamic shared memory, radix-2 stages with a barrier between
+// them.  Serves sizes outside {1024, 2048, 4096}; natural-order tables (ntt.cpp:298-300 indexing).
+template <bool INVERSE>
+__global__ void __launch_bounds__(256) ntt_generic_kernel(uint32_t *__restrict__ data, const uint2 *__restrict__ tw_nat,
+                                                          const LimbConst *__restrict__ lc, uint32_t L, uint32_t logn) {
+    extern __shared__ uint32_t s[];
+    const uint32_t n = 1u << logn;
+    const uint32_t poly = blockIdx.x, limb = poly % L;
+    const LimbConst c = lc[limb];
+    const uint2 *tw = tw_nat + (size_t)limb * n;
+    uint32_t *g = data + (size_t)poly * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[i] = g[i];
+    __syncthreads();
+    if (!INVERSE) {
+        uint32_t tlog = logn - 1;
+        for (uint32_t m = 1; m < n; m <<= 1, tlog--) {
+            for (uint32_t bf = threadIdx.x; bf < n / 2; bf += blockDim.x) {
+                const uint32_t i = bf >> tlog, j = bf & ((1u << tlog) - 1);   // ntt.cpp:292-297
+                const uint32_t a0 = (i << (tlog + 1)) + j;
+                uint32_t x = s[a0], y = s[a0 + (1u << tlog)];
+                ct_bfly(x, y, tw[m + i], c);
+                s[a0] = x; s[a0 + (1u << tlog)] = y;
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = reduce4q(s[i], c);
+    } else {
+        uint32_t tlog = 0;
+        for (uint32_t h = n >> 1; h >= 1; h >>= 1, tlog++) {
+            for (uint32_t bf = threadIdx.x; bf < n / 2; bf += blockDim.x) {
+                const uint32_t i = bf >> tlog, j = bf & ((1u << tlog) - 1);
+                const uint32_t a0 = (i << (tlog + 1)) + j;
+                uint32_t u = s[a0], v = s[a0 + (1u << tlog)];
+                gs_bfly(u, v, tw[h + i], c);
+                s[a0] = u; s[a0 + (1u << tlog)] = v;
+            }
+            __syncthreads();
+        }
+        const uint2 wn = tw[0];   // natural inverse table keeps (n^-1, .) in the unused entry 0
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = csub(shoup_mul(s[i], wn, c.negq), c.negq);
+    }
+}
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256) pointwise_generic_kernel(uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                                const LimbConst *__restrict__ lc, uint32_t L,
+                                                                uint32_t logn, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const LimbConst c = lc[(i >> logn) % L];
+    a[i] = csub(barrett_mul_lazy(a[i], b[i], c), c.neg2q);   // [0,2q): valid inverse input
+}
+
+// ------------------------------------------------------------------------- reference-shaped u64 forward kernel
+// Arithmetic of fwd_ntt_kernel (ntt.cpp:146-159, 292-300, 331-332, 344-363, 368-369, 377-393), including
+// wrap-around mod 2^64 when the tables are not Shoup pairs (main.cpp:49-55 feeds such data).  One CTA per frame
+// (ntt.cpp:579-595 frame layout: low half from `in`, high half from `in2`); work array in dynamic smem when
+// N*8 bytes fits, else in the output buffer itself.
+__global__ void __launch_bounds__(1024) ref_fwd_u64_kernel(const uint64_t *__restrict__ in, const uint64_t *__restrict__ in2,
+                                                           uint64_t *__restrict__ out, const uint64_t *__restrict__ roots,
+                                                           const uint64_t *__restrict__ precons, uint64_t q, uint32_t logn,
+                                                           int use_smem) {
+    extern __shared__ uint64_t s64[];
+    const uint32_t N = 1u << logn;
+    const size_t base = (size_t)blockIdx.x * N;
+    uint64_t *X = use_smem ? s64 : out + base;
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) X[i] = i < N / 2 ? in[base + i] : in2[base + i];
+    __syncthreads();
+    const uint64_t twice = q << 1;
+    uint32_t tlog = logn - 1;
+    for (uint32_t m = 1; m < N; m <<= 1, tlog--) {
+        const bool last = (m == N / 2);
+        for (uint32_t bf = threadIdx.x; bf < N / 2; bf += blockDim.x) {
+            const uint32_t i = bf >> tlog, j = bf & ((1u << tlog) - 1);
+            const uint32_t a0 = (i << (tlog + 1)) + j, a1 = a0 + (1u << tlog);
+            const uint64_t W = roots[m + i], Wp = precons[m + i];
+            uint64_t tx = X[a0];
+            if (tx >= twice) tx -= twice;
+            const uint64_t a = X[a1];
+            const uint64_t c1 = __umul64hi(a, Wp);
+            const uint64_t Q = W * a - c1 * q;
+            uint64_t o0 = tx + Q, o1 = tx + twice - Q;
+            if (last) {
+                if (o0 >= twice) o0 -= twice;
+                if (o0 >= q) o0 -= q;
+                if (o1 >= twice) o1 -= twice;
+                if (o1 >= q) o1 -= q;
+            }
+            X[a0] = o0; X[a1] = o1;
+        }
+        __syncthreads();
+    }
+    if (use_smem)
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = X[i];
+}
+
+// ---------------------------------------------------------------------------------- synthetic data + checksum
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) fill_synthetic_kernel(uint32_t *__restrict__ data, size_t total, uint32_t logn,
+                                                             uint32_t L, const LimbConst *__restrict__ lc, uint64_t seed,
+                                                             uint64_t first_elem) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t q = lc[((first_elem + i) >> logn) % L].q;
+        data[i] = (uint32_t)(splitmix64(seed + first_elem + i) % q);
+    }
+}
+
+__global__ void __launch_bounds__(256) checksum_kernel(const uint32_t *__restrict__ data, size_t count, uint64_t first_index,
+                                                       unsigned long long *__restrict__ sum) {
+    uint64_t acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        acc += splitmix64((first_index + i) * 0xD6E8FEB86659FD93ULL + data[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, (unsigned long long)acc);
+}
+
+}  // namespace agx

@@ -1,0 +1,117 @@
+/*
+ * agxntt.h -- C ABI of the B200-native Agilex-NTT hot path (libagxntt.so).
+ *
+ * Drop-in boundary for joekurina/Agilex-NTT's kernel API (reference = /root/reference):
+ *
+ *   reference interface                                        replaced by
+ *   ---------------------------------------------------------  -------------------------------------------
+ *   ntt_input_kernel(in, in2, modulus, twiddles, precons,      agx_ref_input()      include/kernel/ntt.h:35-41,
+ *                    numFrames, q)                                                   src/kernel/ntt.cpp:508-607
+ *   fwd_ntt_kernel<id>(q)                                      agx_ref_fwd()        include/kernel/ntt.h:32-33,
+ *                                                                                    src/kernel/ntt.cpp:86-506
+ *   ntt_output_kernel(out, numFrames, q)                       agx_ref_output()     include/kernel/ntt.h:43-45,
+ *                                                                                    src/kernel/ntt.cpp:610-640
+ *   sycl::queue::wait()   (src/main.cpp:74)                    agx_wait()
+ *   compile-time FPGA_NTT_SIZE / modulus buffer / twiddle      agx_parms + agx_create()   (the reference has no
+ *   buffers (ntt.h:7-23, main.cpp:32-37)                       parameter struct)
+ *
+ * and the batched u32 entry points BASELINE.json's north_star adds (no reference counterpart):
+ *   agx_ntt_fwd / agx_ntt_inv / agx_polymul on device pointers, *_host variants on host pointers.
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only.  Every function returns 0 (AGX_OK), a negative AGX_E_* code, or a
+ *     positive cudaError_t value.  Nothing throws or aborts across this boundary.  There is NO CPU fallback:
+ *     without a CUDA device agx_create() fails with the cudaError_t.
+ *   - Transform definition (matches ntt.cpp): forward is negacyclic Cooley-Tukey, natural
+ *     order in, BIT-REVERSED order out, outputs fully reduced to [0,q); inverse is Gentleman-Sande,
+ *     bit-reversed in, natural out, n^-1 folded in.  psi = the minimal primitive 2n-th root of unity mod q.
+ *   - Batched layout: uint32_t data[B][L][n] (B polynomials x L RNS limbs), row-major, in place.
+ *     Inputs must be < 2q for the u32 entry points (uniform-mod-q data is < q).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer calls only
+ *     enqueue; completion follows normal stream semantics.  *_host calls return after the results are in
+ *     host memory.
+ *   - A context is bound to one device and is not thread-safe; use one context per host thread / GPU.
+ */
+#ifndef AGXNTT_H
+#define AGXNTT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_OK 0
+#define AGX_E_INVALID (-1)     /* bad argument (null pointer, n not a supported power of two, bad prime ...) */
+#define AGX_E_UNSUPPORTED (-2) /* valid request this build cannot serve */
+#define AGX_E_NOMEM (-3)       /* host allocation failed */
+#define AGX_E_STATE (-4)       /* reference-shaped calls used out of protocol */
+
+typedef struct agx_ctx agx_ctx;
+
+/* Run-time replacement for the reference's compile-time configuration (FPGA_NTT_SIZE ntt.h:7-23, one modulus
+ * buffer main.cpp:34).  n = 2^logn in [8, 32768]; every q[i] prime, < 2^30, q = 1 (mod 2n).  The tuned
+ * register-resident kernels cover n in {1024, 2048, 4096}; other sizes run a generic shared-memory kernel. */
+typedef struct {
+    uint32_t n;
+    uint32_t logn;
+    uint32_t nlimbs;
+    const uint32_t *q; /* [nlimbs] */
+} agx_parms;
+
+/* parms == NULL creates a table-less context usable only with the agx_ref_* calls. */
+int agx_create(agx_ctx **out, const agx_parms *parms, int device);
+int agx_destroy(agx_ctx *ctx);
+
+/* Introspection (parity tests compare these with the oracle's tables). roots/precons in the reference's table
+ * order, ntt.cpp:298-300: entry k = psi^bitrev(k) and floor(entry * 2^32 / q); inverse != 0 -> psi^-1. */
+int agx_get_psi(const agx_ctx *ctx, uint32_t limb, uint32_t *psi);
+int agx_get_tables(const agx_ctx *ctx, uint32_t limb, int inverse, uint32_t *roots, uint32_t *precons);
+
+/* ---- batched u32 transforms on DEVICE pointers, in place, asynchronous on `stream` ---- */
+int agx_ntt_fwd(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
+int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
+/* c = a * b mod (X^n + 1, q_limb): forward(a), forward(b), pointwise, inverse in ONE launch. c may alias a or b. */
+int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
+
+/* ---- the same on HOST pointers: chunked H2D / kernel / D2H pipeline over the context's own streams.
+ * Pinned memory (agx_host_alloc, cudaHostAlloc, cudaHostRegister) is copied directly; pageable memory is staged
+ * through internal pinned buffers.  h_out may equal h_in. ---- */
+int agx_ntt_fwd_host(agx_ctx *ctx, const uint32_t *h_in, uint32_t *h_out, size_t B);
+int agx_ntt_inv_host(agx_ctx *ctx, const uint32_t *h_in, uint32_t *h_out, size_t B);
+int agx_polymul_host(agx_ctx *ctx, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b, size_t B);
+int agx_host_alloc(void **p, size_t bytes);
+int agx_host_free(void *p);
+
+/* ---- synthetic inputs and checksums on the device ----
+ * element g of [B][L][n], counted from polynomial `first_poly`, = splitmix64(seed + g) mod q_limb.
+ * checksum = sum_i splitmix64((first_index + i) * 0xD6E8FEB86659FD93 + data[i]) mod 2^64 (shard sums add up). */
+int agx_fill_synthetic(agx_ctx *ctx, uint32_t *d_data, size_t B, uint64_t seed, size_t first_poly, void *stream);
+int agx_checksum(agx_ctx *ctx, const uint32_t *d_data, size_t count, size_t first_index, uint64_t *h_sum,
+                 void *stream);
+
+/* ---- reference-shaped u64 forward pipeline (host pointers; mirrors main.cpp:60-74) ----
+ * N in {2^2 .. 2^15} (the reference builds 32, 1024, 8192, 16384, 32768: ntt.h:11-20).  Arithmetic is the
+ * reference's u64 Harvey butterfly including wrap-around mod 2^64 for tables that are not Shoup pairs.
+ * The three calls only record/enqueue, in any order (the reference's three kernels run concurrently); the work
+ * runs once all three were made; agx_wait() blocks until `out` is filled (= q.wait()).  `in`, `in2` hold
+ * numFrames*N words (frame b: low half from in[b*N..], high half from in2[b*N + N/2..], ntt.cpp:582-591);
+ * twiddles/precon_twiddles hold N words, modulus 1 word.  Host buffers must stay valid until agx_wait(). */
+int agx_ref_input(agx_ctx *ctx, uint32_t N, const uint64_t *in, const uint64_t *in2, const uint64_t *modulus,
+                  const uint64_t *twiddles, const uint64_t *precon_twiddles, uint32_t numFrames);
+int agx_ref_fwd(agx_ctx *ctx, uint32_t compute_unit_id);
+int agx_ref_output(agx_ctx *ctx, uint64_t *out, int32_t numFrames);
+int agx_wait(agx_ctx *ctx);
+
+/* ---- diagnostics ---- */
+const char *agx_error_string(int code);
+/* kernels this library launched on ctx since creation (bench.py's gpu_launches claim) */
+int agx_launch_count(const agx_ctx *ctx, uint64_t *count);
+/* name of the kernel variant serving (n): "ntt2p<LOGN,LE>" or "generic" */
+int agx_variant(const agx_ctx *ctx, char *buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGXNTT_H */

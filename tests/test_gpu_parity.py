@@ -1,0 +1,378 @@
+"""GPU parity: the CUDA path, called through the C ABI (include/agxntt.h via agilex_ntt_b200.binding), against the
+CPU oracle on identical seeded inputs, the golden outputs recorded from the reference's own code, SURVEY.md App. A
+known answers, and -- at BASELINE.json's full sizes -- full compares plus size-independent properties.
+Bit-exact everywhere (integer work): tolerance = 0."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+Q = O.SEAL_PRIMES_30
+
+
+@pytest.fixture(scope="module")
+def A():
+    import agilex_ntt_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    assert t.cuda.is_available()
+    return t
+
+
+def to_dev(torch, a: np.ndarray):
+    return torch.from_numpy(a.view(np.int32)).cuda()
+
+
+def to_np(t) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint32)
+
+
+_ctx_cache = {}
+
+
+def ctx_for(A, n, primes):
+    key = (n, tuple(primes))
+    if key not in _ctx_cache:
+        _ctx_cache[key] = A.Context(n, primes)
+    return _ctx_cache[key]
+
+
+# ------------------------------------------------------------------------------------------------ tables
+
+@pytest.mark.parametrize("n", [8, 32, 1024, 2048, 4096, 16384, 32768])
+def test_tables_match_oracle(A, n):
+    c = ctx_for(A, n, Q)
+    for l, q in enumerate(Q):
+        assert c.psi(l) == O.min_psi(n, q)
+        for inverse in (False, True):
+            r, p = c.tables(l, inverse)
+            ro, po = O.tables_u32(n, q, inverse=inverse)
+            assert (r == ro).all() and (p == po).all()
+
+
+def test_variants(A):
+    assert ctx_for(A, 4096, Q).variant() == "ntt2p<12,6>"
+    assert ctx_for(A, 2048, Q).variant() == "ntt2p<11,6>"
+    assert ctx_for(A, 1024, Q).variant() == "ntt2p<10,5>"
+    assert ctx_for(A, 32, Q).variant() == "generic"
+
+
+def test_bad_parameters(A):
+    with pytest.raises(A.AgxError):
+        A.Context(4096, [1053818883])          # not prime
+    with pytest.raises(A.AgxError):
+        A.Context(4096, [12289])               # prime, but 12289 != 1 mod 8192
+    with pytest.raises(A.AgxError):
+        A.Context(4000, [Q[0]])                # n not a power of two
+    with pytest.raises(A.AgxError):
+        A.Context(4096, [])                    # no limbs
+
+
+# ------------------------------------------------------------------------------- forward / inverse vs oracle
+
+@pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 32768])
+@pytest.mark.parametrize("L", [1, 3])
+def test_fwd_inv_vs_oracle(A, torch, n, L):
+    primes = Q[:L]
+    c = ctx_for(A, n, primes)
+    P = O.Plan(n, primes)
+    B = 37 if n <= 4096 else 5
+    x = P.synthetic(B, seed=42)
+    d = to_dev(torch, x)
+    c.fwd(d)
+    y = to_np(d).reshape(x.shape)
+    y_ref = P.fwd(x.copy(), variant="barrett")
+    assert (y == y_ref).all()
+    assert (y == P.fwd(x.copy(), variant="shoup")).all()
+    c.inv(d)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    # inverse alone on oracle-produced spectra
+    d2 = to_dev(torch, y_ref)
+    c.inv(d2)
+    assert (to_np(d2).reshape(x.shape) == P.inv(y_ref.copy(), variant="barrett")).all()
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096])
+def test_survey_known_answers(A, torch, n):
+    kat = {
+        (Q[0], 1024): ("dadf656e0db1fcec", "87deb95a0431f1a7"), (Q[0], 2048): ("ef15ec72a1b8f75a", "4c0990d3c733f583"),
+        (Q[0], 4096): ("f06769648ff96d35", "36a1101e7932a140"), (Q[1], 1024): ("f4a32865a5c55bd4", "ddd9d5aed8314f36"),
+        (Q[1], 2048): ("add679a1500a8c8e", "9a0d9a9ff159beef"), (Q[1], 4096): ("43aee98a3e463189", "c01082f426ec6f16"),
+        (Q[2], 1024): ("de6e87421e79aed7", "a04b585d08730040"), (Q[2], 2048): ("d80ea0fd5ba2706e", "8f486de34535d858"),
+        (Q[2], 4096): ("9b587721c09a3c7a", "84177fb9278b7649"),
+    }
+    for q in Q:
+        c = ctx_for(A, n, [q])
+        ramp = np.arange(n, dtype=np.uint32)
+        sm = np.array([O.splitmix64(42 + j) % q for j in range(n)], dtype=np.uint32)
+        d = to_dev(torch, np.stack([ramp, sm]))
+        c.fwd(d)
+        out = to_np(d).reshape(2, n)
+        assert O.sha16(out[0]) == kat[(q, n)][0] and O.sha16(out[1]) == kat[(q, n)][1]
+
+
+def test_simple_vectors(A, torch):
+    """zero -> zero, c*delta -> all c, X -> psi^(2 br(k)+1): the SEAL-Embedded-style checks."""
+    for n in (1024, 2048, 4096):
+        q = Q[1]
+        c = ctx_for(A, n, [q])
+        x = np.zeros((3, n), dtype=np.uint32)
+        x[1, 0] = 7
+        x[2, 1] = 1
+        d = to_dev(torch, x)
+        c.fwd(d)
+        y = to_np(d).reshape(3, n)
+        assert not y[0].any() and (y[1] == 7).all()
+        psi, logn = c.psi(0), n.bit_length() - 1
+        assert y[2].tolist() == [pow(psi, 2 * O.bitrev(k, logn) + 1, q) for k in range(n)]
+
+
+def test_golden_from_reference_code(A, torch, golden):
+    """The u32 GPU path reproduces what the reference's own ntt.cpp produced (tests/golden/make_golden.py)."""
+    g, meta = golden
+    checked = 0
+    for name, m in meta.items():
+        if name.startswith("main_dummy"):
+            continue
+        N, q, psi, kind, frames, seed = int(m[0]), int(m[1]), int(m[2]), m[3], int(m[4]), int(m[5])
+        if kind == "lazy4q":
+            continue   # [0,4q) inputs belong to the u64 reference-shaped path (test_ref_pipeline.py)
+        gidx = np.arange(N * frames, dtype=np.uint64)
+        if kind == "ramp":
+            x = gidx % np.uint64(q)
+        elif kind == "splitmix":
+            x = np.array([O.splitmix64(seed + int(i)) % q for i in gidx], dtype=np.uint64)
+        else:
+            x = np.zeros(N * frames, dtype=np.uint64); x[::N] = 1
+        c = ctx_for(A, N, [q])
+        assert c.psi(0) == psi
+        d = to_dev(torch, x.astype(np.uint32))
+        c.fwd(d)
+        assert (to_np(d) == g[name]).all(), name
+        checked += 1
+    assert checked >= 9
+
+
+def test_edge_inputs(A, torch):
+    n = 4096
+    for L in (1, 3):
+        primes = Q[:L]
+        c = ctx_for(A, n, primes)
+        P = O.Plan(n, primes)
+        qv = np.array(primes, dtype=np.uint32).reshape(1, L, 1)
+        # all q-1 (maximum reduced value)
+        x = np.broadcast_to(qv - 1, (2, L, n)).copy()
+        d = to_dev(torch, x); c.fwd(d)
+        assert (to_np(d).reshape(x.shape) == P.fwd(x.copy())).all()
+        # lazy inputs in [q, 2q) are accepted and mean the same residue
+        base = P.synthetic(2, seed=9)
+        lazy = (base + qv).astype(np.uint32)
+        d = to_dev(torch, lazy); c.fwd(d)
+        assert (to_np(d).reshape(base.shape) == P.fwd(base.copy())).all()
+        d = to_dev(torch, lazy); c.inv(d)
+        assert (to_np(d).reshape(base.shape) == P.inv(base.copy())).all()
+        # empty batch is a no-op
+        e = torch.empty(0, dtype=torch.int32, device="cuda")
+        c.fwd(e); c.inv(e)
+        # B = 1 and a ragged, non-multiple-of-anything batch
+        for B in (1, 149):
+            x = P.synthetic(B, seed=B)
+            d = to_dev(torch, x); c.fwd(d)
+            assert (to_np(d).reshape(x.shape) == P.fwd(x.copy())).all()
+
+
+def test_outputs_always_reduced(A, torch):
+    for n in (1024, 2048, 4096):
+        c = ctx_for(A, n, Q)
+        d = torch.empty(64 * 3 * n, dtype=torch.int32, device="cuda")
+        c.fill_synthetic(d, seed=5)
+        c.fwd(d)
+        y = to_np(d).reshape(64, 3, n)
+        for l, q in enumerate(Q):
+            assert (y[:, l] < q).all()
+        c.inv(d)
+        y = to_np(d).reshape(64, 3, n)
+        for l, q in enumerate(Q):
+            assert (y[:, l] < q).all()
+
+
+# ---------------------------------------------------------------------------------------------------- polymul
+
+@pytest.mark.parametrize("n", [256, 1024, 2048, 4096])
+def test_polymul_vs_oracle_and_schoolbook(A, torch, n):
+    for L in (1, 3):
+        primes = Q[:L]
+        c = ctx_for(A, n, primes)
+        P = O.Plan(n, primes)
+        B = 9
+        a, b = P.synthetic(B, seed=1), P.synthetic(B, seed=2)
+        da, db = to_dev(torch, a), to_dev(torch, b)
+        dc = torch.empty_like(da)
+        c.polymul(dc, da, db)
+        got = to_np(dc).reshape(a.shape)
+        assert (got == P.polymul(a, b)).all()
+        for l, q in enumerate(primes):
+            assert (got[0, l] == O.polymul_schoolbook(a[0, l], b[0, l], q)).all()
+        assert (to_np(da).reshape(a.shape) == a).all() and (to_np(db).reshape(a.shape) == b).all()
+        if n >= 1024:   # in place over a (the tuned kernel allows aliasing)
+            c.polymul(da, da, db)
+            assert (to_np(da).reshape(a.shape) == got).all()
+
+
+def test_polymul_kat(A, torch):
+    n, q = 2048, Q[0]
+    c = ctx_for(A, n, [q])
+    a = np.arange(1, n + 1, dtype=np.uint32)
+    b = (2 * np.arange(n) + 1).astype(np.uint32)
+    da, db = to_dev(torch, a), to_dev(torch, b)
+    dc = torch.empty_like(da)
+    c.polymul(dc, da, db)
+    r = to_np(dc)
+    assert r[:4].tolist() == [291855365, 287667213, 283483167, 279303231] and O.sha16(r) == "cc989f874ebe7af7"
+    e1 = np.zeros(n, dtype=np.uint32); e1[n - 1] = 1
+    e2 = np.zeros(n, dtype=np.uint32); e2[1] = 1
+    c.polymul(dc, to_dev(torch, e1), to_dev(torch, e2))
+    r = to_np(dc)
+    assert r[0] == q - 1 and not r[1:].any()      # X^(n-1) * X = -1
+
+
+# ---------------------------------------------------------------------------- synthetic fill, checksum, host API
+
+def test_device_fill_and_checksum_match_oracle(A, torch):
+    n = 2048
+    c = ctx_for(A, n, Q)
+    P = O.Plan(n, Q)
+    d = torch.empty(11 * 3 * n, dtype=torch.int32, device="cuda")
+    c.fill_synthetic(d, seed=1234, first_poly=5)
+    x = P.synthetic(11, seed=1234, first_poly=5)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    assert c.checksum(d, first_index=77) == O.checksum_u32(x, first_index=77)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_entry_points(A, torch, pinned):
+    n = 4096
+    c = ctx_for(A, n, Q)
+    P = O.Plan(n, Q)
+    B = 1500                      # > one 32 MiB chunk of the pipeline (=682 polys at L=3): exercises slot reuse
+    x = P.synthetic(B, seed=3)
+    want = P.fwd(x.copy(), threads=O.max_threads())
+    if pinned:
+        src = torch.from_numpy(x.view(np.int32)).pin_memory()
+        dst = torch.empty_like(src).pin_memory()
+        c.fwd_host(src, dst)
+        assert (dst.numpy().view(np.uint32) == want).all()
+        c.inv_host(dst)
+        assert (dst.numpy().view(np.uint32) == x).all()
+    else:
+        out = np.empty_like(x)
+        c.fwd_host(x, out)
+        assert (out == want).all()
+        c.inv_host(out)           # in place
+        assert (out == x).all()
+
+
+def test_polymul_host(A, torch):
+    n = 2048
+    c = ctx_for(A, n, Q[:1])
+    P = O.Plan(n, Q[:1])
+    a, b = P.synthetic(300, seed=11), P.synthetic(300, seed=12)
+    out = np.empty_like(a)
+    c.polymul_host(out, a, b)
+    assert (out == P.polymul(a, b, threads=O.max_threads())).all()
+
+
+def test_launch_count_counts(A, torch):
+    c = ctx_for(A, 4096, Q[:1])
+    d = torch.zeros(4 * 4096, dtype=torch.int32, device="cuda")
+    before = c.launch_count()
+    c.fwd(d); c.inv(d)
+    assert c.launch_count() == before + 2
+
+
+# ------------------------------------------------------------------- BASELINE.json configs at their full sizes
+
+def _full_compare(A, torch, n, primes, B, seed):
+    c = ctx_for(A, n, primes)
+    P = O.Plan(n, primes)
+    L = len(primes)
+    d = torch.empty(B * L * n, dtype=torch.int32, device="cuda")
+    c.fill_synthetic(d, seed=seed)
+    chk_in = c.checksum(d)
+    c.fwd(d)
+    y = to_np(d).reshape(B, L, n)
+    x = P.synthetic(B, seed=seed)
+    assert O.checksum_u32(x) == chk_in
+    want = P.fwd(x, threads=O.max_threads())          # in place on x
+    assert (y == want).all()
+    for l, q in enumerate(primes):
+        assert int(y[:, l].max()) < q
+    c.inv(d)
+    assert c.checksum(d) == chk_in                    # round trip at full size: checksum of the whole batch
+    del d
+    torch.cuda.empty_cache()
+
+
+def test_config2_n4096_b65536_full(A, torch):
+    """configs[1]: n=4096, single prime, 65,536 polynomials (1 GiB), full bit-exact compare + round trip."""
+    _full_compare(A, torch, 4096, Q[:1], 65536, 42)
+
+
+def test_config3_rns3_b32768_full(A, torch):
+    """configs[2]: n=4096, 3-limb RNS, batch 32,768: bit-exact vs the oracle per limb (full compare)."""
+    _full_compare(A, torch, 4096, Q, 32768, 42)
+
+
+def test_config4_polymul_n2048_b131072(A, torch):
+    """configs[3]: negacyclic polymul n=2048, batch 131,072: 64-polynomial sample vs exact schoolbook, full batch vs
+    the CPU NTT-path oracle, plus linearity (a*(b1+b2) = a*b1 + a*b2) as a size-independent property."""
+    n, q, B = 2048, Q[0], 131072
+    c = ctx_for(A, n, [q])
+    P = O.Plan(n, [q])
+    da = torch.empty(B * n, dtype=torch.int32, device="cuda")
+    db = torch.empty_like(da)
+    dc = torch.empty_like(da)
+    c.fill_synthetic(da, seed=1234)
+    c.fill_synthetic(db, seed=99)
+    c.polymul(dc, da, db)
+    got = to_np(dc).reshape(B, 1, n)
+    a, b = P.synthetic(B, seed=1234), P.synthetic(B, seed=99)
+    idx = np.linspace(0, B - 1, 64).astype(int)
+    for i in idx:
+        assert (got[i, 0] == O.polymul_schoolbook(a[i, 0], b[i, 0], q)).all()
+    want = P.polymul(a, b, threads=O.max_threads())
+    assert (got == want).all()
+    del want
+    # linearity on the first 4096 products
+    m = 4096 * n
+    b2 = torch.empty(m, dtype=torch.int32, device="cuda"); c.fill_synthetic(b2, seed=7)
+    bs = ((db[:m].long() + b2.long()) % q).int()
+    c1 = torch.empty(m, dtype=torch.int32, device="cuda"); c.polymul(c1, da[:m].contiguous(), bs)
+    c2 = torch.empty(m, dtype=torch.int32, device="cuda"); c.polymul(c2, da[:m].contiguous(), b2)
+    assert ((dc[:m].long() + c2.long()) % q == c1.long()).all()
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_config5_sizes_roundtrip_large(A, torch, n):
+    """configs[4] sweep sizes: 2^28/n polynomials (1 GiB) per GPU, round trip + sampled oracle compare."""
+    B = (1 << 28) // n
+    c = ctx_for(A, n, Q[:1])
+    P = O.Plan(n, Q[:1])
+    d = torch.empty(B * n, dtype=torch.int32, device="cuda")
+    c.fill_synthetic(d, seed=1234)
+    chk = c.checksum(d)
+    c.fwd(d)
+    lo = to_np(d[: 512 * n]).reshape(512, 1, n)
+    hi = to_np(d[(B - 512) * n:]).reshape(512, 1, n)
+    assert (lo == P.fwd(P.synthetic(512, seed=1234))).all()
+    assert (hi == P.fwd(P.synthetic(512, seed=1234, first_poly=B - 512))).all()
+    c.inv(d)
+    assert c.checksum(d) == chk

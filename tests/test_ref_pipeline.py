@@ -1,0 +1,103 @@
+"""The reference-shaped u64 forward pipeline (agx_ref_input / agx_ref_fwd / agx_ref_output / agx_wait), driven
+with main.cpp's call sequence (src/main.cpp:60-74), against the C restatement of ntt.cpp and the golden outputs
+recorded from the reference's own code.  Bit-exact, including wrap-around mod 2^64 on main.cpp's dummy data."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    import agilex_ntt_b200 as pkg
+    return pkg
+
+
+def run_pipeline(A, in1, in2, modulus, tw, pre, frames, order=("input", "fwd", "output")):
+    p = A.RefPipeline()
+    out = np.zeros(len(tw) * frames, dtype=np.uint64)
+    for step in order:
+        if step == "input":
+            p.ntt_input_kernel(in1, in2, np.array([modulus], dtype=np.uint64), tw, pre, frames)
+        elif step == "fwd":
+            p.fwd_ntt_kernel(0)
+        else:
+            p.ntt_output_kernel(out, frames)
+    p.wait()
+    n_launch = p.launch_count()
+    p.close()
+    return out, n_launch
+
+
+def test_main_cpp_dummy_data(A, golden):
+    """main.cpp:49-55: in[i]=i, in2[i]=i+1, twiddle[i]=i+2, precon[i]=i+3, modulus 65537, N=16384, 1 frame."""
+    g, meta = golden
+    N = 16384
+    i = np.arange(N, dtype=np.uint64)
+    out, launches = run_pipeline(A, i, i + 1, 65537, i + 2, i + 3, 1)
+    assert launches == 1
+    assert (out == g["main_dummy_u64"]).all()
+    assert hashlib.sha256(out.tobytes()).hexdigest() == meta["main_dummy_sha256_le64"][0]
+    txt = "".join("%d\n" % int(v) for v in out)      # what main.cpp:82 prints
+    assert hashlib.sha256(txt.encode()).hexdigest() == \
+        "68db50a07a87d4e18387a721d88b42291198aba2f9e9138e2e52d45ad6537c5c"
+
+
+@pytest.mark.parametrize("N", [32, 1024, 8192, 16384, 32768])
+def test_reference_sizes_vs_restatement(A, N):
+    q = O.SEAL_PRIMES_30[1]
+    tw, pre = O.tables_u64(N, q)
+    frames = 3 if N <= 8192 else 2
+    x = np.array([O.splitmix64(1000 + i) % (4 * q) for i in range(N * frames)], dtype=np.uint64)   # lazy [0,4q)
+    x2 = np.array([O.splitmix64(5000 + i) % q for i in range(N * frames)], dtype=np.uint64)
+    out, _ = run_pipeline(A, x, x2, q, tw, pre, frames)
+    assert (out == O.ref_fwd_u64(x, x2, q, tw, pre, frames)).all()
+    assert (out < q).all()
+
+
+def test_golden_lazy_and_multiframe(A, golden):
+    g, meta = golden
+    for name in ("n1024_lazy", "n1024_sm_f4", "n32_sm_f3", "n8192_sm"):
+        m = meta[name]
+        N, q, psi, kind, frames, seed = int(m[0]), int(m[1]), int(m[2]), m[3], int(m[4]), int(m[5])
+        mod = 4 * q if kind == "lazy4q" else q
+        x = np.array([O.splitmix64(seed + i) % mod for i in range(N * frames)], dtype=np.uint64)
+        tw, pre = O.tables_u64(N, q, psi)
+        out, _ = run_pipeline(A, x, x, q, tw, pre, frames)
+        assert (out == g[name]).all(), name
+
+
+def test_call_order_is_free_like_the_reference(A):
+    """The reference's three kernels run concurrently and meet through pipes; submission order does not matter."""
+    N, q = 1024, O.SEAL_PRIMES_30[0]
+    tw, pre = O.tables_u64(N, q)
+    x = np.arange(N, dtype=np.uint64)
+    want = O.ref_fwd_u64(x, x, q, tw, pre, 1)
+    for order in (("output", "input", "fwd"), ("fwd", "output", "input"), ("input", "output", "fwd")):
+        out, _ = run_pipeline(A, x, x, q, tw, pre, 1, order)
+        assert (out == want).all()
+
+
+def test_protocol_errors(A):
+    p = A.RefPipeline()
+    N, q = 32, O.SEAL_PRIMES_30[0]
+    tw, pre = O.tables_u64(N, q)
+    x = np.arange(N, dtype=np.uint64)
+    p.ntt_input_kernel(x, x, np.array([q], dtype=np.uint64), tw, pre, 1)
+    with pytest.raises(A.AgxError):            # a second input before the round completed
+        p.ntt_input_kernel(x, x, np.array([q], dtype=np.uint64), tw, pre, 1)
+    with pytest.raises(A.AgxError):            # waiting on a round that can never complete
+        p.wait()
+    with pytest.raises(A.AgxError):            # only compute unit 0 exists (ntt.cpp:648)
+        p.fwd_ntt_kernel(1)
+    # frame-count mismatch between loader and drain
+    out = np.zeros(N * 2, dtype=np.uint64)
+    p.ntt_input_kernel(x, x, np.array([q], dtype=np.uint64), tw, pre, 1)
+    p.fwd_ntt_kernel(0)
+    with pytest.raises(A.AgxError):
+        p.ntt_output_kernel(out, 2)
+    p.close()
