@@ -28,7 +28,7 @@ class _Parms(C.Structure):
 
 
 def _load() -> C.CDLL:
-    path = _build.LIB
+    path = os.environ.get("AGX_LIB", _build.LIB)   # AGX_LIB: experiment builds of the same ABI (kernel variants)
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the CUDA extension is mandatory; there is no CPU fallback)")

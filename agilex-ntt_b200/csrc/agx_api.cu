@@ -20,6 +20,10 @@ using namespace agx;
 
 namespace {
 
+#ifndef AGX_PPC
+#define AGX_PPC 1
+#endif
+
 constexpr int kSlots = 3;                          // host pipeline depth (H2D / kernel / D2H in flight)
 constexpr size_t kChunkBytes = 32u << 20;          // per-slot chunk of the host pipeline
 
@@ -53,6 +57,7 @@ struct agx_ctx {
     std::vector<uint32_t> q, psi;
     std::vector<NaturalTables> nat_fwd, nat_inv;
     uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural when le == 0)
+    uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
     unsigned long long *d_sum = nullptr;
     uint64_t launches = 0;
@@ -91,7 +96,8 @@ int set_device(const agx_ctx *c) { CK(cudaSetDevice(c->device)); return AGX_OK; 
 
 int build_tables(agx_ctx *c) {
     const uint32_t n = c->n, L = c->L;
-    std::vector<uint2> hf((size_t)L * n), hi((size_t)L * n);
+    std::vector<uint2> hf((size_t)L * n), hi((size_t)L * n), cf((size_t)L * n, make_uint2(0, 0)), ci((size_t)L * n, make_uint2(0, 0));
+    const uint32_t lt = c->le ? c->logn - c->le : 0, tpp = 1u << lt;
     std::vector<LimbConst> lc(L);
     for (uint32_t l = 0; l < L; l++) {
         const uint32_t q = c->q[l];
@@ -109,6 +115,15 @@ int build_tables(agx_ctx *c) {
             if (k == 1 && c->le) w = (uint32_t)mulmod_u64(w, ninv, q);  // last GS stage folds n^-1 (two-pass kernels)
             hi[(size_t)l * n + pos] = make_uint2(w, shoup_companion(w, q));
         }
+        if (c->le) {   // column-pass tables: local stage j, pair h sits where the row pass of thread 0 looks
+            for (int j = 0; j < c->le; j++)
+                for (uint32_t g = 0; g < (1u << j); g++) {
+                    const uint32_t nat = (1u << j) + g;
+                    const uint32_t pos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (g >> 1) * tpp) + (g & 1);
+                    cf[(size_t)l * n + pos] = make_uint2(c->nat_fwd[l].w[nat], c->nat_fwd[l].wp[nat]);
+                    ci[(size_t)l * n + pos] = make_uint2(c->nat_inv[l].w[nat], c->nat_inv[l].wp[nat]);
+                }
+        }
         int k = 0;
         while ((1ull << k) <= q) k++;                                   // bit length of q
         LimbConst &x = lc[l];
@@ -116,7 +131,7 @@ int build_tables(agx_ctx *c) {
         const uint64_t mu = (uint64_t)((((unsigned __int128)1) << (2 * k)) / q);
         x.bar_mu = (uint32_t)(mu << (31 - k));
         x.bar_sh = (uint32_t)(k - 1);
-        x.psi = psi; x.pad = 0;
+        x.psi = psi; x.zero = 0;
     }
     CK(cudaMalloc(&c->d_tw_fwd, hf.size() * sizeof(uint2)));
     CK(cudaMalloc(&c->d_tw_inv, hi.size() * sizeof(uint2)));
@@ -125,10 +140,16 @@ int build_tables(agx_ctx *c) {
     CK(cudaMemcpy(c->d_tw_fwd, hf.data(), hf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_tw_inv, hi.data(), hi.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
+    if (c->le) {
+        CK(cudaMalloc(&c->d_twc_fwd, cf.size() * sizeof(uint2)));
+        CK(cudaMalloc(&c->d_twc_inv, ci.size() * sizeof(uint2)));
+        CK(cudaMemcpy(c->d_twc_fwd, cf.data(), cf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_twc_inv, ci.data(), ci.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     return AGX_OK;
 }
 
-KParams kparams(const agx_ctx *c) { return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_lc, c->L}; }
+KParams kparams(const agx_ctx *c) { return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L}; }
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
@@ -136,9 +157,18 @@ template <int LOGN, int LE>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     using G = Geo<LOGN, LE>;
     const KParams p = kparams(c);
+    constexpr int PPC = AGX_PPC;
     const dim3 grid((unsigned)T), block(G::TPP);
-    if (op == OP_FWD) ntt_fwd_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p);
-    else if (op == OP_INV) ntt_inv_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p);
+    const dim3 grid_t((unsigned)((T + PPC - 1) / PPC)), block_t(G::TPP * PPC);
+    constexpr size_t smem = (size_t)PPC * G::N * 4;
+    static bool attr_done = false;                   // one flag per <LOGN, LE> instantiation
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(ntt_fwd_loop_kernel<LOGN, LE, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(ntt_inv_loop_kernel<LOGN, LE, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    if (op == OP_FWD) ntt_fwd_loop_kernel<LOGN, LE, PPC><<<grid_t, block_t, smem, s>>>(out, p, (uint32_t)T);
+    else if (op == OP_INV) ntt_inv_loop_kernel<LOGN, LE, PPC><<<grid_t, block_t, smem, s>>>(out, p, (uint32_t)T);
     else polymul_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
     c->launches++;
     return (int)cudaGetLastError();
@@ -379,7 +409,8 @@ int agx_destroy(agx_ctx *c) {
     RefState &R = c->ref;
     cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out); cudaFree(R.d_tw); cudaFree(R.d_pre);
     if (R.stream) cudaStreamDestroy(R.stream);
-    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_lc); cudaFree(c->d_sum);
+    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
+    cudaFree(c->d_lc); cudaFree(c->d_sum);
     delete c;
     return AGX_OK;
 }

@@ -22,7 +22,9 @@ struct LimbConst {
     uint32_t bar_mu;   // floor(2^(2k)/q) << (31-k), k = bit length of q  (pointwise Barrett)
     uint32_t bar_sh;   // k - 1
     uint32_t psi;
-    uint32_t pad;
+    uint32_t zero;     // always 0, but only known at run time: a third IADD3 operand that keeps two-input adds off
+                       // the multiply pipe (ptxas otherwise turns half of them into IMAD.IADD, and IMAD is the
+                       // binding pipe of this kernel -- see DESIGN.md "integer roofline")
 };
 
 // min(x - m, x) as unsigned: x - m if x >= m else x.  One VIADDMNMX.U32 on sm_90+ (DPX), `negm` = 2^32 - m.
@@ -37,13 +39,13 @@ __device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint2 w, uint32_t negq
 __device__ __forceinline__ void ct_bfly(uint32_t &x, uint32_t &y, uint2 w, const LimbConst &c) {
     const uint32_t tx = csub(x, c.neg2q);          // ntt.cpp:331-332
     const uint32_t Q = shoup_mul(y, w, c.negq);    // ntt.cpp:344-363
-    x = tx + Q;                                    // ntt.cpp:368
+    x = tx + Q + c.zero;                           // ntt.cpp:368  (three-input form: stays an IADD3)
     y = tx + c.twoq - Q;                           // ntt.cpp:369
 }
 
 // Gentleman-Sande (inverse) butterfly: u,v in [0,2q) -> u + v, (u - v)*w, both in [0,2q).
 __device__ __forceinline__ void gs_bfly(uint32_t &u, uint32_t &v, uint2 w, const LimbConst &c) {
-    const uint32_t s = u + v;
+    const uint32_t s = u + v + c.zero;
     const uint32_t d = u + c.twoq - v;
     u = csub(s, c.neg2q);
     v = shoup_mul(d, w, c.negq);
@@ -51,7 +53,7 @@ __device__ __forceinline__ void gs_bfly(uint32_t &u, uint32_t &v, uint2 w, const
 
 // Last inverse stage with n^-1 folded in: wn = (n^-1, .), w1n = (iroot[1] * n^-1, .); outputs in [0,q).
 __device__ __forceinline__ void gs_bfly_last(uint32_t &u, uint32_t &v, uint2 wn, uint2 w1n, const LimbConst &c) {
-    const uint32_t s = u + v;
+    const uint32_t s = u + v + c.zero;
     const uint32_t d = u + c.twoq - v;
     u = csub(shoup_mul(s, wn, c.negq), c.negq);
     v = csub(shoup_mul(d, w1n, c.negq), c.negq);

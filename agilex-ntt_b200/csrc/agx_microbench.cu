@@ -89,6 +89,69 @@ int run(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cu
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Instruction-supply test: a straight-line body of K instructions (alternating IMAD / IADD3 on 8 chains, which the
+// mix test above shows can issue at 1 warp-instruction/clk/scheduler) executed `reps` times by W warps per
+// scheduler.  desync != 0 delays each CTA of an SM by a different amount so the warps sit at different program
+// counters -- the situation of independent polynomial teams in the NTT kernels.  Reports warp-instr/clk/scheduler.
+template <int K>
+__global__ void __launch_bounds__(128) icache_kernel(uint32_t *out, long long *cycles, int reps, int desync,
+                                                     unsigned *sm_slot) {
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 31u + i;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    __shared__ unsigned slot;
+    if (threadIdx.x == 0) slot = atomicAdd(&sm_slot[smid], 1u);
+    __syncthreads();
+    if (desync) {
+        const long long until = clock64() + (long long)slot * desync;
+        while (clock64() < until) {}
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++) {
+#pragma unroll
+        for (int u = 0; u < K / 16; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(a[(i + 1) & 7]), "r"(a[(i + 3) & 7]));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(a[(i + 4) & 7]) : "r"(a[(i + 5) & 7]));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int K>
+int run_icache(int sms, uint32_t *d_out, long long *d_cyc, unsigned *d_slot, cudaStream_t s) {
+    const long long total_instr = 1 << 21;                 // per warp
+    const int reps = (int)(total_instr / K);
+    for (int wps = 1; wps <= 4; wps *= 2) {                // warps per scheduler = CTAs per SM (4 warps per CTA)
+        for (int desync = 0; desync <= 1; desync++) {
+            const int ctas = sms * wps;
+            CK(cudaMemsetAsync(d_slot, 0, sizeof(unsigned) * 256, s));
+            icache_kernel<K><<<ctas, 128, 0, s>>>(d_out, d_cyc, reps, desync ? 3000 + K : 0, d_slot);
+            CK(cudaStreamSynchronize(s));
+            CK(cudaGetLastError());
+            std::vector<long long> cyc(ctas);
+            CK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * ctas, cudaMemcpyDeviceToHost));
+            std::sort(cyc.begin(), cyc.end());
+            const double med = (double)cyc[ctas / 2];
+            printf("{\"test\": \"icache\", \"body_instr\": %d, \"body_kb\": %.1f, \"warps_per_sched\": %d, \"desync\": %d, "
+                   "\"warp_instr_per_clk_per_sched\": %.3f}\n",
+                   K, K * 16 / 1024.0, wps, desync, (double)reps * K * wps / med);
+        }
+    }
+    return 0;
+}
+
 int main() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -96,7 +159,7 @@ int main() {
     printf("{\"device\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\"}\n", prop.name, sms, prop.major, prop.minor);
     uint32_t *d_out; long long *d_cyc;
     CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * 1024));
-    CK(cudaMalloc(&d_cyc, sizeof(long long) * sms));
+    CK(cudaMalloc(&d_cyc, sizeof(long long) * sms * 8));
     const uint32_t q = 1053818881u;
     agx::LimbConst lc{q, 2 * q, 0u - q, 0u - 2 * q, 0, 29, 0, 0};
     cudaStream_t s;
@@ -111,5 +174,14 @@ int main() {
     if (run<T_BFLY_CT>(sms, d_out, d_cyc, lc, s)) return 1;
     if (run<T_BFLY_GS>(sms, d_out, d_cyc, lc, s)) return 1;
     if (run<T_SHFL>(sms, d_out, d_cyc, lc, s)) return 1;
+    unsigned *d_slot;
+    CK(cudaMalloc(&d_slot, sizeof(unsigned) * 256));
+    if (run_icache<128>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<256>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<512>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<1024>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<2048>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<4096>(sms, d_out, d_cyc, d_slot, s)) return 1;
+    if (run_icache<8192>(sms, d_out, d_cyc, d_slot, s)) return 1;
     return 0;
 }

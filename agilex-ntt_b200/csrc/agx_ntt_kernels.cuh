@@ -31,6 +31,8 @@ namespace agx {
 struct KParams {
     const uint2 *tw_fwd;     // [L][n] kernel order
     const uint2 *tw_inv;     // [L][n] kernel order
+    const uint2 *twc_fwd;    // [L][n] column-pass copy: stage j < LE twiddles at the offsets the row pass uses
+    const uint2 *twc_inv;
     const LimbConst *lc;     // [L]
     uint32_t L;
 };
@@ -315,6 +317,181 @@ polymul_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const
         x[4 * cc + 3] = csub(barrett_mul_lazy(av.w, reduce4q(x[4 * cc + 3], c), c), c.neg2q);
     }
     inv_core<LOGN, LE>(x, out + off, sm, twi, c, tid);
+}
+
+
+// ------------------------------------------------------------------------------ looped two-pass kernels
+// The fully unrolled passes above are ~47 KB of SASS per kernel; with 16 warps per SM each at a different point
+// of that straight-line code the instruction caches thrash (ncu: stall_no_instruction 2.7 per issue, the top
+// stall).  Both passes of a transform apply the SAME register pairing pattern to x[0..E): stage j pairs
+// x[k] with x[k + (E/2 >> j)].  Only the twiddle addressing differs, and that is affine in three per-pass
+// values (sbase, tstride, toff).  So the kernels below run ONE copy of the stage code inside a 2-trip loop,
+// which halves the code footprint and lets it stay resident in the SM's instruction cache.
+//   pass over columns (uniform twiddles): sbase = 0,  tstride = 1,   toff = 0
+//   pass over rows (per-thread twiddles): sbase = LT, tstride = TPP, toff = tid
+//   twiddle (local stage j >= 1, group g) lives at uint4 index (1 << (sbase+j-1)) + (g>>1)*tstride + toff,
+//   twiddle (j = 0) at uint2 index (1 << sbase) + toff.
+// When LT < LE (n = 2048) the row pass has only LE-1... LT stages: local stage 0 is skipped there (j0 = LE-LT).
+
+// Per-pass twiddle base pointers.  Every twiddle load of the shared stage code is `base + compile-time offset`:
+//   row pass   : table = tw (kernel order), b4 = (uint4*)tw + tid,  b2 = tw + (1<<LT) + tid
+//   column pass: table = twc (the same offsets, populated only where a thread with tid = 0 would look), b4, b2 alike
+// so the loop body contains no address arithmetic (an earlier version computed base + h*stride at run time, which
+// ptxas turned into IMAD.WIDE -- on the pipe this kernel is bound by).
+struct PassAddr {
+    const uint4 *b4;
+    const uint2 *b2;
+};
+
+template <int LOGN, int LE>
+__device__ __forceinline__ PassAddr pass_addr(const uint2 *__restrict__ table, uint32_t toff) {
+    return PassAddr{reinterpret_cast<const uint4 *>(table) + toff, table + (1u << (LOGN - LE)) + toff};
+}
+
+template <int LOGN, int LE, int J>
+__device__ __forceinline__ void load_tw_generic(uint2 (&w)[1 << J], const PassAddr &a) {
+    constexpr int LT = LOGN - LE, TPP = 1 << LT;
+    if constexpr (J == 0) {
+        w[0] = __ldg(a.b2);
+    } else {
+#pragma unroll
+        for (int h = 0; h < (1 << (J - 1)); h++) {
+            const uint4 v = __ldg(a.b4 + ((1 << (LT + J - 1)) + h * TPP));
+            w[2 * h] = make_uint2(v.x, v.y);
+            w[2 * h + 1] = make_uint2(v.z, v.w);
+        }
+    }
+}
+
+template <int LOGN, int LE, int J>
+__device__ __forceinline__ void ct_stage(uint32_t (&x)[1 << LE], const PassAddr &a, const LimbConst &c) {
+    constexpr int half = (1 << LE) >> (J + 1);
+    uint2 w[1 << J];
+    load_tw_generic<LOGN, LE, J>(w, a);
+#pragma unroll
+    for (int g = 0; g < (1 << J); g++)
+#pragma unroll
+        for (int i = 0; i < half; i++) ct_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], w[g], c);
+}
+
+template <int LOGN, int LE, int J>
+__device__ __forceinline__ void gs_stage(uint32_t (&x)[1 << LE], const PassAddr &a, const LimbConst &c) {
+    constexpr int half = (1 << LE) >> (J + 1);
+    uint2 w[1 << J];
+    load_tw_generic<LOGN, LE, J>(w, a);
+#pragma unroll
+    for (int g = 0; g < (1 << J); g++)
+#pragma unroll
+        for (int i = 0; i < half; i++) gs_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], w[g], c);
+}
+
+template <int LOGN, int LE, int J>
+__device__ __forceinline__ void ct_stages_from(uint32_t (&x)[1 << LE], const PassAddr &a, const LimbConst &c) {
+    ct_stage<LOGN, LE, J>(x, a, c);
+    if constexpr (J + 1 < LE) ct_stages_from<LOGN, LE, J + 1>(x, a, c);
+}
+
+template <int LOGN, int LE, int J>
+__device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const PassAddr &a, const LimbConst &c) {
+    gs_stage<LOGN, LE, J>(x, a, c);
+    if constexpr (J > 1) gs_stages_down_to1<LOGN, LE, J - 1>(x, a, c);
+}
+
+// PPC = polynomials per CTA.  PPC == 1: one CTA per polynomial, per-polynomial barrier.  PPC > 1: the CTA's
+// PPC polynomial teams meet at __syncthreads(), which keeps all warps of the CTA at nearly the same program
+// counter so they share instruction-cache lines.
+template <int TPP, int PPC>
+__device__ __forceinline__ void team_sync() {
+    if constexpr (PPC == 1) poly_sync<TPP>(); else __syncthreads();
+}
+
+template <int LOGN, int LE, int PPC>
+__global__ void __launch_bounds__(PPC << (LOGN - LE), (AGX_MINB(LOGN, LE) / PPC) > 0 ? (AGX_MINB(LOGN, LE) / PPC) : 1)
+ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
+    using G = Geo<LOGN, LE>;
+    extern __shared__ uint4 agx_dyn_smem[];          // PPC * N/4 chunks (dynamic: PPC*16 KB can exceed 48 KB)
+    const uint32_t slot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
+    uint4 *sm = agx_dyn_smem + slot * (G::N / 4);
+    uint32_t poly = blockIdx.x * PPC + slot;
+    const bool active = poly < T;
+    if (!active) poly = T - 1;                       // inactive team: compute on valid memory, store nothing
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
+    const uint2 *twc = p.twc_fwd + (size_t)limb * G::N;
+    uint32_t *g = data + (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        PassAddr a;
+        if (pass == 0) {
+            a = pass_addr<LOGN, LE>(twc, 0u);
+#pragma unroll
+            for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
+        } else {
+            a = pass_addr<LOGN, LE>(tw, tid);
+            lds_row<LOGN, LE>(sm, x, tid);
+        }
+        if (G::LT == LE || pass == 0) ct_stage<LOGN, LE, 0>(x, a, c);
+        ct_stages_from<LOGN, LE, 1>(x, a, c);
+        if (pass == 0) {
+            sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
+            team_sync<G::TPP, PPC>();
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+    sts_row<LOGN, LE>(sm, x, tid);
+    team_sync<G::TPP, PPC>();
+    if (active) smem_to_global<LOGN, LE>(sm, g, tid);
+}
+
+template <int LOGN, int LE, int PPC>
+__global__ void __launch_bounds__(PPC << (LOGN - LE), (AGX_MINB(LOGN, LE) / PPC) > 0 ? (AGX_MINB(LOGN, LE) / PPC) : 1)
+ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
+    using G = Geo<LOGN, LE>;
+    extern __shared__ uint4 agx_dyn_smem[];          // PPC * N/4 chunks (dynamic: PPC*16 KB can exceed 48 KB)
+    const uint32_t slot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
+    uint4 *sm = agx_dyn_smem + slot * (G::N / 4);
+    uint32_t poly = blockIdx.x * PPC + slot;
+    const bool active = poly < T;
+    if (!active) poly = T - 1;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *tw = p.tw_inv + (size_t)limb * G::N;
+    const uint2 *twc = p.twc_inv + (size_t)limb * G::N;
+    uint32_t *g = data + (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+    global_to_smem<LOGN, LE>(sm, g, tid);
+    team_sync<G::TPP, PPC>();
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        PassAddr a;
+        if (pass == 0) {
+            a = pass_addr<LOGN, LE>(tw, tid);
+            lds_row<LOGN, LE>(sm, x, tid);
+        } else {
+            a = pass_addr<LOGN, LE>(twc, 0u);
+            lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
+        }
+        gs_stages_down_to1<LOGN, LE, LE - 1>(x, a, c);
+        if (pass == 0) {
+            if (G::LT == LE) gs_stage<LOGN, LE, 0>(x, a, c);
+            sts_row<LOGN, LE>(sm, x, tid);
+            team_sync<G::TPP, PPC>();
+        }
+    }
+    {   // last stage (global stage 0) with n^-1 folded: tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .)
+        const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1);
+#pragma unroll
+        for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
+    }
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
+    }
 }
 
 // ---------------------------------------------------------------------------------- generic (any n) u32 kernels
