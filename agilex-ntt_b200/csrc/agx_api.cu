@@ -60,6 +60,7 @@ struct agx_ctx {
     uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
     unsigned long long *d_sum = nullptr;
+    unsigned long long *d_trace = nullptr;                 // AGX_TRACE builds: phase timestamps of sampled CTAs
     uint64_t launches = 0;
     HostPipe pipe;
     RefState ref;
@@ -137,6 +138,10 @@ int build_tables(agx_ctx *c) {
     CK(cudaMalloc(&c->d_tw_inv, hi.size() * sizeof(uint2)));
     CK(cudaMalloc(&c->d_lc, lc.size() * sizeof(LimbConst)));
     CK(cudaMalloc(&c->d_sum, sizeof(unsigned long long)));
+#if AGX_TRACE
+    CK(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 16 * 4096));
+    CK(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 16 * 4096));
+#endif
     CK(cudaMemcpy(c->d_tw_fwd, hf.data(), hf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_tw_inv, hi.data(), hi.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
@@ -149,7 +154,9 @@ int build_tables(agx_ctx *c) {
     return AGX_OK;
 }
 
-KParams kparams(const agx_ctx *c) { return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L}; }
+KParams kparams(const agx_ctx *c) {
+    return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->d_trace};
+}
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
@@ -410,7 +417,7 @@ int agx_destroy(agx_ctx *c) {
     cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out); cudaFree(R.d_tw); cudaFree(R.d_pre);
     if (R.stream) cudaStreamDestroy(R.stream);
     cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
-    cudaFree(c->d_lc); cudaFree(c->d_sum);
+    cudaFree(c->d_lc); cudaFree(c->d_sum); cudaFree(c->d_trace);
     delete c;
     return AGX_OK;
 }
@@ -554,6 +561,13 @@ const char *agx_error_string(int code) {
 int agx_launch_count(const agx_ctx *c, uint64_t *count) {
     if (!c || !count) return AGX_E_INVALID;
     *count = c->launches;
+    return AGX_OK;
+}
+
+// AGX_TRACE builds only (deliberately not in the public header): phase timestamps of the last forward launch
+int agx_debug_trace(const agx_ctx *c, unsigned long long *out, size_t count) {
+    if (!c || !c->d_trace || !out || count > 16 * 4096) return AGX_E_UNSUPPORTED;
+    CK(cudaMemcpy(out, c->d_trace, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return AGX_OK;
 }
 

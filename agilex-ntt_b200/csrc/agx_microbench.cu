@@ -66,12 +66,12 @@ __global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long
 }
 
 template <int TEST>
-int run(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cudaStream_t s) {
-    bench_kernel<TEST><<<sms, 1024, 0, s>>>(d_out, d_cyc, 12345u, lc);   // warm-up
+int run(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cudaStream_t s, int threads = 1024) {
+    bench_kernel<TEST><<<sms, threads, 0, s>>>(d_out, d_cyc, 12345u, lc);   // warm-up
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
-    bench_kernel<TEST><<<sms, 1024, 0, s>>>(d_out, d_cyc, 12345u, lc);
+    bench_kernel<TEST><<<sms, threads, 0, s>>>(d_out, d_cyc, 12345u, lc);
     CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -81,11 +81,11 @@ int run(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cu
     CK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
     std::sort(cyc.begin(), cyc.end());
     const double med = (double)cyc[sms / 2];
-    const double steps = (double)ITERS * UN * CH * 1024.0;          // per SM
+    const double steps = (double)ITERS * UN * CH * (double)threads;  // per SM
     const double lane_instr = steps * kInstrPerStep[TEST];
-    printf("{\"test\": \"%s\", \"lane_instr_per_clk_per_sm\": %.2f, \"units_per_clk_per_sm\": %.3f, \"median_cycles\": %.0f, "
+    printf("{\"test\": \"%s\", \"warps_per_sched\": %d, \"lane_instr_per_clk_per_sm\": %.2f, \"units_per_clk_per_sm\": %.3f, \"median_cycles\": %.0f, "
            "\"event_ms\": %.4f, \"implied_sm_mhz\": %.0f}\n",
-           kNames[TEST], lane_instr / med, steps / med, med, ms, med / (ms * 1e3));
+           kNames[TEST], threads / 128, lane_instr / med, steps / med, med, ms, med / (ms * 1e3));
     return 0;
 }
 
@@ -174,6 +174,10 @@ int main() {
     if (run<T_BFLY_CT>(sms, d_out, d_cyc, lc, s)) return 1;
     if (run<T_BFLY_GS>(sms, d_out, d_cyc, lc, s)) return 1;
     if (run<T_SHFL>(sms, d_out, d_cyc, lc, s)) return 1;
+    for (int thr = 128; thr <= 1024; thr *= 2) {      // the butterfly at 1, 2, 4, 8 warps per scheduler
+        if (run<T_BFLY_CT>(sms, d_out, d_cyc, lc, s, thr)) return 1;
+        if (run<T_MIX_IMAD_IADD3>(sms, d_out, d_cyc, lc, s, thr)) return 1;
+    }
     unsigned *d_slot;
     CK(cudaMalloc(&d_slot, sizeof(unsigned) * 256));
     if (run_icache<128>(sms, d_out, d_cyc, d_slot, s)) return 1;

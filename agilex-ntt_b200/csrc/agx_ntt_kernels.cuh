@@ -35,7 +35,23 @@ struct KParams {
     const uint2 *twc_inv;
     const LimbConst *lc;     // [L]
     uint32_t L;
+    unsigned long long *trace;   // AGX_TRACE builds only: per-CTA phase timestamps (profiles/trace_phases.py)
 };
+
+// Timing-experiment switches (never set in the shipped library):
+//   AGX_TRACE=1   thread 0 of every 64th CTA stamps clock64() at phase boundaries of the forward kernel
+//   AGX_ABLATE=k  bit0 no global loads, bit1 no stores/staging, bit2 no smem transpose, bit4 no final reduction
+#ifndef AGX_TRACE
+#define AGX_TRACE 0
+#endif
+#ifndef AGX_ABLATE
+#define AGX_ABLATE 0
+#endif
+#if AGX_TRACE
+#define AGX_STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x % 64) == 5) p.trace[(blockIdx.x / 64) * 16 + (i)] = clock64(); } while (0)
+#else
+#define AGX_STAMP(i) do { } while (0)
+#endif
 
 template <int LOGN, int LE>
 struct Geo {
@@ -56,6 +72,22 @@ __host__ __device__ constexpr uint32_t tw_pos(int s, uint32_t T, uint32_t kk) {
     constexpr uint32_t TPP = 1u << LT;
     const uint32_t c = 1u << (s - LT);
     return c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * TPP + T) * 2 + (kk & 1);
+}
+
+// L2 prefetch of the polynomial a CTA slot will work on one wave later.  The CTA that owns it then finds its 16 KB in
+// L2 (~250 clk) instead of paying a loaded-HBM round trip (~1.8 us measured as the load wait in the phase trace).
+#ifndef AGX_PREFETCH_DIST
+#define AGX_PREFETCH_DIST (8 * 148)
+#endif
+template <int LOGN, int TPP>
+__device__ __forceinline__ void prefetch_ahead(const uint32_t *g_this, uint32_t poly, uint32_t T, uint32_t tid) {
+    constexpr int LINES = (4 << LOGN) / 128;                 // 128-byte lines per polynomial
+    if (AGX_PREFETCH_DIST > 0 && poly + AGX_PREFETCH_DIST < T) {
+        const char *nxt = reinterpret_cast<const char *>(g_this) + (size_t)AGX_PREFETCH_DIST * (4u << LOGN);
+#pragma unroll
+        for (int i = 0; i < (LINES + TPP - 1) / TPP; i++)
+            if (i * TPP + tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)(i * TPP + tid) * 128));
+    }
 }
 
 template <int TPP>
@@ -422,29 +454,76 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     uint32_t *g = data + (size_t)poly * G::N;
 
     uint32_t x[G::E];
+#ifdef AGX_STAGGER
+    if (blockIdx.x < 8u * 148u) {                    // first wave only: de-phase the CTAs that share an SM
+        const long long until = clock64() + (long long)(blockIdx.x / 148u) * AGX_STAGGER;
+        while (clock64() < until) {}
+    }
+#endif
+    AGX_STAMP(0);
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         PassAddr a;
         if (pass == 0) {
+#if AGX_ABLATE & 32
+            a = pass_addr<LOGN, LE>(tw, tid);            // experiment: column pass with row-style (per-thread) loads
+#else
             a = pass_addr<LOGN, LE>(twc, 0u);
+#endif
+#if AGX_ABLATE & 1
+#pragma unroll
+            for (int k = 0; k < G::E; k++) x[k] = tid * 977u + k * 131071u + poly;
+#else
 #pragma unroll
             for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
+#endif
+            prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
         } else {
+#if AGX_ABLATE & 8
+            a = pass_addr<LOGN, LE>(twc, 0u);            // experiment: row pass with column-style (uniform) loads
+#else
             a = pass_addr<LOGN, LE>(tw, tid);
+#endif
+#if !(AGX_ABLATE & 4)
             lds_row<LOGN, LE>(sm, x, tid);
+#endif
         }
         if (G::LT == LE || pass == 0) ct_stage<LOGN, LE, 0>(x, a, c);
+        AGX_STAMP(1 + 7 * pass);                     // stage 0 done (pass 0: includes the wait for the global loads)
+#if AGX_TRACE
+        ct_stage<LOGN, LE, 1>(x, a, c); AGX_STAMP(2 + 7 * pass);
+        ct_stage<LOGN, LE, 2>(x, a, c); AGX_STAMP(3 + 7 * pass);
+        ct_stage<LOGN, LE, 3>(x, a, c); AGX_STAMP(4 + 7 * pass);
+        ct_stage<LOGN, LE, 4>(x, a, c); AGX_STAMP(5 + 7 * pass);
+        if constexpr (LE > 5) ct_stage<LOGN, LE, LE - 1>(x, a, c);
+        AGX_STAMP(6 + 7 * pass);
+#else
         ct_stages_from<LOGN, LE, 1>(x, a, c);
+#endif
         if (pass == 0) {
+#if !(AGX_ABLATE & 4)
             sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
+#endif
             team_sync<G::TPP, PPC>();
+            AGX_STAMP(7);
         }
     }
+#if !(AGX_ABLATE & 16)
 #pragma unroll
     for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+#endif
+#if AGX_ABLATE & 2
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < G::E; j++) acc ^= x[j];
+    if (acc == 0x12345678u) g[tid] = acc;            // ablation: keep the math alive, store (almost) nothing
+#else
     sts_row<LOGN, LE>(sm, x, tid);
     team_sync<G::TPP, PPC>();
+    AGX_STAMP(14);
     if (active) smem_to_global<LOGN, LE>(sm, g, tid);
+    AGX_STAMP(15);
+#endif
 }
 
 template <int LOGN, int LE, int PPC>
@@ -465,6 +544,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 
     uint32_t x[G::E];
     global_to_smem<LOGN, LE>(sm, g, tid);
+    prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
     team_sync<G::TPP, PPC>();
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
