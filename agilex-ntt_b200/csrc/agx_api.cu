@@ -20,10 +20,6 @@ using namespace agx;
 
 namespace {
 
-#ifndef AGX_PPC
-#define AGX_PPC 1
-#endif
-
 constexpr int kSlots = 3;                          // host pipeline depth (H2D / kernel / D2H in flight)
 constexpr size_t kChunkBytes = 32u << 20;          // per-slot chunk of the host pipeline
 
@@ -51,6 +47,7 @@ struct RefState {
 
 struct agx_ctx {
     int device = 0;
+    int sms = 148;
     bool has_parms = false;
     uint32_t n = 0, logn = 0, L = 0;
     int le = 0;                                    // 0 = generic kernel
@@ -164,19 +161,10 @@ template <int LOGN, int LE>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     using G = Geo<LOGN, LE>;
     const KParams p = kparams(c);
-    constexpr int PPC = AGX_PPC;
     const dim3 grid((unsigned)T), block(G::TPP);
-    const dim3 grid_t((unsigned)((T + PPC - 1) / PPC)), block_t(G::TPP * PPC);
-    constexpr size_t smem = (size_t)PPC * G::N * 4;
-    static bool attr_done = false;                   // one flag per <LOGN, LE> instantiation
-    if (!attr_done) {
-        CK(cudaFuncSetAttribute(ntt_fwd_loop_kernel<LOGN, LE, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(ntt_inv_loop_kernel<LOGN, LE, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    if (op == OP_FWD) ntt_fwd_loop_kernel<LOGN, LE, PPC><<<grid_t, block_t, smem, s>>>(out, p, (uint32_t)T);
-    else if (op == OP_INV) ntt_inv_loop_kernel<LOGN, LE, PPC><<<grid_t, block_t, smem, s>>>(out, p, (uint32_t)T);
-    else polymul_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
+    if (op == OP_FWD) ntt_fwd_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, (uint32_t)T);
+    else if (op == OP_INV) ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, (uint32_t)T);
+    else polymul_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -393,6 +381,7 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
     agx_ctx *c = new (std::nothrow) agx_ctx();
     if (!c) return AGX_E_NOMEM;
     c->device = device;
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
     if (parms) {
         if (!parms->q || parms->nlimbs == 0 || parms->nlimbs > 64 || parms->logn < 3 || parms->logn > 15 ||
             parms->n != (1u << parms->logn)) { delete c; return AGX_E_INVALID; }

@@ -6,6 +6,7 @@
 // stream of the instruction under test on 8 independent register chains; cycles are SM clock64() deltas, so the
 // result is lane-operations per clock per SM, independent of DVFS.
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <vector>
 #include <algorithm>
@@ -19,11 +20,25 @@ constexpr int CH = 8;        // independent chains per thread
 constexpr int UN = 16;       // unrolled repetitions of the chain set per loop iteration
 constexpr int ITERS = 256;
 
-enum Test { T_IMAD, T_IMADHI, T_IMADWIDE, T_VIADDMNMX, T_IADD3, T_LOP3, T_MIX_IMAD_IADD3, T_BFLY_CT, T_BFLY_GS, T_SHFL, T_COUNT };
+enum Test { T_IMAD, T_IMADHI, T_IMADWIDE, T_VIADDMNMX, T_IADD3, T_LOP3, T_MIX_IMAD_IADD3, T_BFLY_CT, T_BFLY_GS, T_SHFL, T_DFMA, T_BFLY_CT_FP64, T_BFLY_CT_HYBRID, T_COUNT };
 static const char *kNames[] = {"imad_lo", "imad_hi", "imad_wide", "viaddmnmx_u32", "iadd3", "lop3", "mix_imad+iadd3",
-                               "ct_butterfly", "gs_butterfly", "shfl_xor"};
+                               "ct_butterfly", "gs_butterfly", "shfl_xor", "dfma", "ct_butterfly_fp64q", "ct_butterfly_hybrid"};
 // lane-instructions issued per inner step per chain (for instr/clk) and "units" (butterflies) per step
-static const int kInstrPerStep[] = {1, 1, 1, 1, 1, 1, 2, 6, 6, 1};
+static const int kInstrPerStep[] = {1, 1, 1, 1, 1, 1, 2, 6, 6, 1, 1, 7, 6};
+
+// Butterfly whose Shoup quotient comes from the FP64 pipe instead of IMAD.HI (which runs at half rate):
+// L = low word of fma.rm((2^52 + y), sigma, 2^52 - 2^52*sigma), sigma = fl_down(1 + w/q); then
+// Q = y*(w+q) + L*(-q) mod 2^32 lies in [0,2q) exactly like the Shoup form (checked exhaustively-at-random on the host).
+__device__ __forceinline__ void ct_bfly_fp64q(uint32_t &x, uint32_t &y, uint32_t wt, double sigma, double cc,
+                                              const agx::LimbConst &c) {
+    const uint32_t tx = agx::csub(x, c.neg2q);
+    const double dy = __hiloint2double(0x43300000, (int)y);
+    const double r = __fma_rd(dy, sigma, cc);
+    const uint32_t L = (uint32_t)__double2loint(r);
+    const uint32_t Q = y * wt + L * c.negq;
+    x = tx + Q + c.zero;
+    y = tx + c.twoq - Q;
+}
 
 template <int TEST>
 __global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long *cycles, uint32_t seed, agx::LimbConst lc) {
@@ -31,6 +46,10 @@ __global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long
 #pragma unroll
     for (int i = 0; i < CH; i++) { a[i] = seed + threadIdx.x * 977u + i * 131u; b[i] = (seed ^ 0x9e3779b9u) + i * 7919u + threadIdx.x; }
     const uint2 w = make_uint2(seed | 1u, seed * 3u + 5u);
+    const double sigma = 1.0 + (double)(seed & 0xffff) / 65536.0, cc = 4503599627370496.0 * (1.0 - sigma);
+    double dacc[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) dacc[i] = 1.0 + i + threadIdx.x;
     __syncthreads();
     const long long t0 = clock64();
     for (int it = 0; it < ITERS; it++) {
@@ -53,6 +72,12 @@ __global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long
                 } else if (TEST == T_BFLY_CT) agx::ct_bfly(a[i], b[i], w, lc);
                 else if (TEST == T_BFLY_GS) agx::gs_bfly(a[i], b[i], w, lc);
                 else if (TEST == T_SHFL) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1 + (i & 15));
+                else if (TEST == T_DFMA) dacc[i] = __fma_rd(dacc[i], sigma, cc);
+                else if (TEST == T_BFLY_CT_FP64) ct_bfly_fp64q(a[i], b[i], w.x, sigma, cc, lc);
+                else if (TEST == T_BFLY_CT_HYBRID) {
+                    if (i & 1) ct_bfly_fp64q(a[i], b[i], w.x, sigma, cc, lc);
+                    else agx::ct_bfly(a[i], b[i], w, lc);
+                }
             }
         }
     }
@@ -60,7 +85,7 @@ __global__ void __launch_bounds__(1024, 1) bench_kernel(uint32_t *out, long long
     const long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < CH; i++) acc ^= a[i] ^ b[i];
+    for (int i = 0; i < CH; i++) acc ^= a[i] ^ b[i] ^ (uint32_t)__double2loint(dacc[i]);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -178,6 +203,12 @@ int main() {
         if (run<T_BFLY_CT>(sms, d_out, d_cyc, lc, s, thr)) return 1;
         if (run<T_MIX_IMAD_IADD3>(sms, d_out, d_cyc, lc, s, thr)) return 1;
     }
+    if (run<T_DFMA>(sms, d_out, d_cyc, lc, s)) return 1;
+    for (int thr = 256; thr <= 1024; thr *= 2) {
+        if (run<T_BFLY_CT_FP64>(sms, d_out, d_cyc, lc, s, thr)) return 1;
+        if (run<T_BFLY_CT_HYBRID>(sms, d_out, d_cyc, lc, s, thr)) return 1;
+    }
+    if (getenv("AGX_MB_SKIP_ICACHE")) return 0;
     unsigned *d_slot;
     CK(cudaMalloc(&d_slot, sizeof(unsigned) * 256));
     if (run_icache<128>(sms, d_out, d_cyc, d_slot, s)) return 1;

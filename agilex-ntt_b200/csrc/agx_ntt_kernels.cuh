@@ -41,6 +41,7 @@ struct KParams {
 // Timing-experiment switches (never set in the shipped library):
 //   AGX_TRACE=1   thread 0 of every 64th CTA stamps clock64() at phase boundaries of the forward kernel
 //   AGX_ABLATE=k  bit0 no global loads, bit1 no stores/staging, bit2 no smem transpose, bit4 no final reduction
+//                 (results of these experiments: profiles/r01_experiments.md)
 #ifndef AGX_TRACE
 #define AGX_TRACE 0
 #endif
@@ -163,194 +164,14 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
     }
 }
 
-// ------------------------------------------------------------------------------------------------- the passes
-
-// forward pass A: stages 0..LE-1 on x[k] = elem[tid + TPP*k]; twiddle index 2^s + (k >> (LE-s)) (uniform)
-template <int LE>
-__device__ __forceinline__ void fwd_pass_a(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, const LimbConst &c) {
-#pragma unroll
-    for (int s = 0; s < LE; s++) {
-        const int half = (1 << LE) >> (s + 1);
-#pragma unroll
-        for (int g = 0; g < (1 << s); g++) {
-            const uint2 w = __ldg(tw + (1 << s) + g);
-#pragma unroll
-            for (int j = 0; j < half; j++) ct_bfly(x[g * 2 * half + j], x[g * 2 * half + j + half], w, c);
-        }
-    }
-}
-
-// twiddles of (stage s, thread T): c = 2^(s-LT) pairs, fetched as coalesced 16-byte loads
-template <int LOGN, int LE, int S>
-__device__ __forceinline__ void load_stage_tw(uint2 (&w)[1 << (S - (LOGN - LE))], const uint2 *__restrict__ tw,
-                                              uint32_t T) {
-    constexpr int LT = LOGN - LE, C = 1 << (S - LT), TPP = 1 << LT;
-    if constexpr (C == 1) {
-        w[0] = __ldg(tw + (1 << S) + T);
-    } else {
-        const uint4 *t4 = reinterpret_cast<const uint4 *>(tw + (1 << S));
-#pragma unroll
-        for (int h = 0; h < C / 2; h++) {
-            const uint4 v = __ldg(t4 + h * TPP + T);
-            w[2 * h] = make_uint2(v.x, v.y);
-            w[2 * h + 1] = make_uint2(v.z, v.w);
-        }
-    }
-}
-
-template <int LOGN, int LE, int S>
-__device__ __forceinline__ void fwd_stage_b(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, uint32_t T,
-                                            const LimbConst &c) {
-    constexpr int LT = LOGN - LE, C = 1 << (S - LT), half = 1 << (LOGN - 1 - S);
-    uint2 w[C];
-    load_stage_tw<LOGN, LE, S>(w, tw, T);
-#pragma unroll
-    for (int kk = 0; kk < C; kk++)
-#pragma unroll
-        for (int j = 0; j < half; j++) ct_bfly(x[kk * 2 * half + j], x[kk * 2 * half + j + half], w[kk], c);
-    if constexpr (S + 1 < LOGN) fwd_stage_b<LOGN, LE, S + 1>(x, tw, T, c);
-}
-
-template <int LOGN, int LE, int S>
-__device__ __forceinline__ void inv_stage_b(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, uint32_t T,
-                                            const LimbConst &c) {
-    constexpr int LT = LOGN - LE, C = 1 << (S - LT), half = 1 << (LOGN - 1 - S);
-    uint2 w[C];
-    load_stage_tw<LOGN, LE, S>(w, tw, T);
-#pragma unroll
-    for (int kk = 0; kk < C; kk++)
-#pragma unroll
-        for (int j = 0; j < half; j++) gs_bfly(x[kk * 2 * half + j], x[kk * 2 * half + j + half], w[kk], c);
-    if constexpr (S > LE) inv_stage_b<LOGN, LE, S - 1>(x, tw, T, c);
-}
-
-// inverse pass A': stages LE-1 .. 1 then stage 0 with n^-1 folded (tw[0] = n^-1, tw[1] = iroot1 * n^-1)
-template <int LE>
-__device__ __forceinline__ void inv_pass_a(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw, const LimbConst &c) {
-#pragma unroll
-    for (int s = LE - 1; s >= 1; s--) {
-        const int half = (1 << LE) >> (s + 1);
-#pragma unroll
-        for (int g = 0; g < (1 << s); g++) {
-            const uint2 w = __ldg(tw + (1 << s) + g);
-#pragma unroll
-            for (int j = 0; j < half; j++) gs_bfly(x[g * 2 * half + j], x[g * 2 * half + j + half], w, c);
-        }
-    }
-    const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1);
-#pragma unroll
-    for (int j = 0; j < (1 << LE) / 2; j++) gs_bfly_last(x[j], x[j + (1 << LE) / 2], wn, w1n, c);
-}
-
-// ---- whole-polynomial cores shared by the three kernels -----------------------------------------------------
-
-// global (natural order) -> registers as rows: x[j] = NTT(poly)[E*tid + j], values in [0,4q)
-template <int LOGN, int LE>
-__device__ __forceinline__ void fwd_core(uint32_t (&x)[1 << LE], const uint32_t *__restrict__ g, uint4 *sm,
-                                         const uint2 *__restrict__ tw, const LimbConst &c, uint32_t tid) {
-    using G = Geo<LOGN, LE>;
-#pragma unroll
-    for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
-    fwd_pass_a<LE>(x, tw, c);
-    sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
-    poly_sync<G::TPP>();
-    lds_row<LOGN, LE>(sm, x, tid);
-    fwd_stage_b<LOGN, LE, LE>(x, tw, tid, c);
-}
-
-// registers as rows (values < 2q) -> global natural order, fully reduced
-template <int LOGN, int LE>
-__device__ __forceinline__ void inv_core(uint32_t (&x)[1 << LE], uint32_t *__restrict__ g, uint4 *sm,
-                                         const uint2 *__restrict__ tw, const LimbConst &c, uint32_t tid) {
-    using G = Geo<LOGN, LE>;
-    inv_stage_b<LOGN, LE, LOGN - 1>(x, tw, tid, c);
-    sts_row<LOGN, LE>(sm, x, tid);
-    poly_sync<G::TPP>();
-    lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
-    inv_pass_a<LE>(x, tw, c);
-#pragma unroll
-    for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
-}
-
-// ------------------------------------------------------------------------------------------------- the kernels
-
-#ifndef AGX_MINB
-#define AGX_MINB(LOGN, LE) ((1 << (LE)) >= 64 ? (512 >> ((LOGN) - (LE))) : (768 >> ((LOGN) - (LE))))
+// minimum resident CTAs per SM requested from ptxas (sets the register cap): 64 coefficients/thread -> 512 threads
+// per SM (128 registers each), 32 coefficients/thread -> 768 threads (85 registers).
+#ifndef AGX_THREADS_E64
+#define AGX_THREADS_E64 512
 #endif
-
-template <int LOGN, int LE>
-__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-ntt_fwd_kernel(uint32_t *__restrict__ data, KParams p) {
-    using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t poly = blockIdx.x;
-    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
-    const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
-    uint32_t *g = data + (size_t)poly * G::N;
-
-    uint32_t x[G::E];
-    fwd_core<LOGN, LE>(x, g, sm, tw, c, tid);
-#pragma unroll
-    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
-    sts_row<LOGN, LE>(sm, x, tid);       // own row only: no barrier needed before
-    poly_sync<G::TPP>();
-    smem_to_global<LOGN, LE>(sm, g, tid);
-}
-
-template <int LOGN, int LE>
-__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-ntt_inv_kernel(uint32_t *__restrict__ data, KParams p) {
-    using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t poly = blockIdx.x;
-    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
-    const uint2 *tw = p.tw_inv + (size_t)limb * G::N;
-    uint32_t *g = data + (size_t)poly * G::N;
-
-    uint32_t x[G::E];
-    global_to_smem<LOGN, LE>(sm, g, tid);
-    poly_sync<G::TPP>();
-    lds_row<LOGN, LE>(sm, x, tid);
-    inv_core<LOGN, LE>(x, g, sm, tw, c, tid);
-}
-
-template <int LOGN, int LE>
-__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-polymul_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
-               KParams p) {
-    using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
-    __shared__ uint4 park[G::N / 4];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t poly = blockIdx.x;
-    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
-    const uint2 *twf = p.tw_fwd + (size_t)limb * G::N;
-    const uint2 *twi = p.tw_inv + (size_t)limb * G::N;
-    const size_t off = (size_t)poly * G::N;
-
-    uint32_t x[G::E];
-    fwd_core<LOGN, LE>(x, a + off, sm, twf, c, tid);
-#pragma unroll
-    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
-    sts_row<LOGN, LE>(park, x, tid);     // NTT(a), own row, read back by the same thread only
-    poly_sync<G::TPP>();                 // everyone is done reading `sm` rows before b's columns overwrite them
-    fwd_core<LOGN, LE>(x, b + off, sm, twf, c, tid);
-#pragma unroll
-    for (int cc = 0; cc < G::CPR; cc++) {
-        const uint4 av = park[tid * G::CPR + (cc ^ (tid & G::SW))];
-        x[4 * cc + 0] = csub(barrett_mul_lazy(av.x, reduce4q(x[4 * cc + 0], c), c), c.neg2q);
-        x[4 * cc + 1] = csub(barrett_mul_lazy(av.y, reduce4q(x[4 * cc + 1], c), c), c.neg2q);
-        x[4 * cc + 2] = csub(barrett_mul_lazy(av.z, reduce4q(x[4 * cc + 2], c), c), c.neg2q);
-        x[4 * cc + 3] = csub(barrett_mul_lazy(av.w, reduce4q(x[4 * cc + 3], c), c), c.neg2q);
-    }
-    inv_core<LOGN, LE>(x, out + off, sm, twi, c, tid);
-}
-
+#ifndef AGX_MINB
+#define AGX_MINB(LOGN, LE) ((1 << (LE)) >= 64 ? (AGX_THREADS_E64 >> ((LOGN) - (LE))) : (768 >> ((LOGN) - (LE))))
+#endif
 
 // ------------------------------------------------------------------------------ looped two-pass kernels
 // The fully unrolled passes above are ~47 KB of SASS per kernel; with 16 warps per SM each at a different point
@@ -429,24 +250,13 @@ __device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const
     if constexpr (J > 1) gs_stages_down_to1<LOGN, LE, J - 1>(x, a, c);
 }
 
-// PPC = polynomials per CTA.  PPC == 1: one CTA per polynomial, per-polynomial barrier.  PPC > 1: the CTA's
-// PPC polynomial teams meet at __syncthreads(), which keeps all warps of the CTA at nearly the same program
-// counter so they share instruction-cache lines.
-template <int TPP, int PPC>
-__device__ __forceinline__ void team_sync() {
-    if constexpr (PPC == 1) poly_sync<TPP>(); else __syncthreads();
-}
-
-template <int LOGN, int LE, int PPC>
-__global__ void __launch_bounds__(PPC << (LOGN - LE), (AGX_MINB(LOGN, LE) / PPC) > 0 ? (AGX_MINB(LOGN, LE) / PPC) : 1)
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
-    extern __shared__ uint4 agx_dyn_smem[];          // PPC * N/4 chunks (dynamic: PPC*16 KB can exceed 48 KB)
-    const uint32_t slot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
-    uint4 *sm = agx_dyn_smem + slot * (G::N / 4);
-    uint32_t poly = blockIdx.x * PPC + slot;
-    const bool active = poly < T;
-    if (!active) poly = T - 1;                       // inactive team: compute on valid memory, store nothing
+    __shared__ uint4 sm[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
     const LimbConst c = p.lc[limb];
     const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
@@ -454,22 +264,12 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     uint32_t *g = data + (size_t)poly * G::N;
 
     uint32_t x[G::E];
-#ifdef AGX_STAGGER
-    if (blockIdx.x < 8u * 148u) {                    // first wave only: de-phase the CTAs that share an SM
-        const long long until = clock64() + (long long)(blockIdx.x / 148u) * AGX_STAGGER;
-        while (clock64() < until) {}
-    }
-#endif
     AGX_STAMP(0);
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         PassAddr a;
-        if (pass == 0) {
-#if AGX_ABLATE & 32
-            a = pass_addr<LOGN, LE>(tw, tid);            // experiment: column pass with row-style (per-thread) loads
-#else
+        if (pass == 0) {                             // column pass: x[k] = poly[tid + TPP*k], stages 0..LE-1
             a = pass_addr<LOGN, LE>(twc, 0u);
-#endif
 #if AGX_ABLATE & 1
 #pragma unroll
             for (int k = 0; k < G::E; k++) x[k] = tid * 977u + k * 131071u + poly;
@@ -478,12 +278,8 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
             for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
 #endif
             prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
-        } else {
-#if AGX_ABLATE & 8
-            a = pass_addr<LOGN, LE>(twc, 0u);            // experiment: row pass with column-style (uniform) loads
-#else
+        } else {                                     // row pass: x[j] = poly[E*tid + j], stages LE..logn-1
             a = pass_addr<LOGN, LE>(tw, tid);
-#endif
 #if !(AGX_ABLATE & 4)
             lds_row<LOGN, LE>(sm, x, tid);
 #endif
@@ -504,7 +300,7 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 #if !(AGX_ABLATE & 4)
             sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
 #endif
-            team_sync<G::TPP, PPC>();
+            poly_sync<G::TPP>();
             AGX_STAMP(7);
         }
     }
@@ -518,24 +314,21 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     for (int j = 0; j < G::E; j++) acc ^= x[j];
     if (acc == 0x12345678u) g[tid] = acc;            // ablation: keep the math alive, store (almost) nothing
 #else
-    sts_row<LOGN, LE>(sm, x, tid);
-    team_sync<G::TPP, PPC>();
+    sts_row<LOGN, LE>(sm, x, tid);                   // own row only: no barrier needed before
+    poly_sync<G::TPP>();
     AGX_STAMP(14);
-    if (active) smem_to_global<LOGN, LE>(sm, g, tid);
+    smem_to_global<LOGN, LE>(sm, g, tid);
     AGX_STAMP(15);
 #endif
 }
 
-template <int LOGN, int LE, int PPC>
-__global__ void __launch_bounds__(PPC << (LOGN - LE), (AGX_MINB(LOGN, LE) / PPC) > 0 ? (AGX_MINB(LOGN, LE) / PPC) : 1)
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
-    extern __shared__ uint4 agx_dyn_smem[];          // PPC * N/4 chunks (dynamic: PPC*16 KB can exceed 48 KB)
-    const uint32_t slot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
-    uint4 *sm = agx_dyn_smem + slot * (G::N / 4);
-    uint32_t poly = blockIdx.x * PPC + slot;
-    const bool active = poly < T;
-    if (!active) poly = T - 1;
+    __shared__ uint4 sm[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
     const LimbConst c = p.lc[limb];
     const uint2 *tw = p.tw_inv + (size_t)limb * G::N;
@@ -545,14 +338,14 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     uint32_t x[G::E];
     global_to_smem<LOGN, LE>(sm, g, tid);
     prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
-    team_sync<G::TPP, PPC>();
+    poly_sync<G::TPP>();
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         PassAddr a;
-        if (pass == 0) {
+        if (pass == 0) {                             // row pass: stages logn-1 .. LE
             a = pass_addr<LOGN, LE>(tw, tid);
             lds_row<LOGN, LE>(sm, x, tid);
-        } else {
+        } else {                                     // column pass: stages LE-1 .. 1 (stage 0 below)
             a = pass_addr<LOGN, LE>(twc, 0u);
             lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
         }
@@ -560,7 +353,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
         if (pass == 0) {
             if (G::LT == LE) gs_stage<LOGN, LE, 0>(x, a, c);
             sts_row<LOGN, LE>(sm, x, tid);
-            team_sync<G::TPP, PPC>();
+            poly_sync<G::TPP>();
         }
     }
     {   // last stage (global stage 0) with n^-1 folded: tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .)
@@ -568,10 +361,86 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 #pragma unroll
         for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
     }
-    if (active) {
 #pragma unroll
-        for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
+    for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
+}
+
+// Fused negacyclic product c = a * b mod (X^n + 1, q): forward(a), forward(b), pointwise, inverse in ONE launch
+// (BASELINE.json config 4).  The forward stage code runs 4 times (2 operands x 2 passes) and the inverse stage code
+// twice, each from a single copy; NTT(a) waits in a second shared-memory buffer (own row per thread) while b is
+// transformed.  HBM traffic: 3 * n * 4 bytes per product.
+template <int LOGN, int LE>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, KParams p) {
+    using G = Geo<LOGN, LE>;
+    __shared__ uint4 sm[G::N / 4];
+    __shared__ uint4 park[G::N / 4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    const LimbConst c = p.lc[limb];
+    const uint2 *twf = p.tw_fwd + (size_t)limb * G::N, *twfc = p.twc_fwd + (size_t)limb * G::N;
+    const uint2 *twi = p.tw_inv + (size_t)limb * G::N, *twic = p.twc_inv + (size_t)limb * G::N;
+    const size_t off = (size_t)poly * G::N;
+
+    uint32_t x[G::E];
+#pragma unroll 1
+    for (int opnd = 0; opnd < 2; opnd++) {
+        const uint32_t *src = (opnd == 0 ? a : b) + off;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            PassAddr ad;
+            if (pass == 0) {
+                ad = pass_addr<LOGN, LE>(twfc, 0u);
+#pragma unroll
+                for (int k = 0; k < G::E; k++) x[k] = __ldcs(src + tid + G::TPP * k);
+            } else {
+                ad = pass_addr<LOGN, LE>(twf, tid);
+                lds_row<LOGN, LE>(sm, x, tid);
+            }
+            if (G::LT == LE || pass == 0) ct_stage<LOGN, LE, 0>(x, ad, c);
+            ct_stages_from<LOGN, LE, 1>(x, ad, c);
+            if (pass == 0) {
+                poly_sync<G::TPP>();                 // all rows of the previous operand have been read
+                sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
+                poly_sync<G::TPP>();
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+        if (opnd == 0) sts_row<LOGN, LE>(park, x, tid);   // NTT(a): written and later read by this thread only
     }
+#pragma unroll
+    for (int cc = 0; cc < G::CPR; cc++) {            // pointwise: NTT(a) .* NTT(b), lazily reduced to [0,2q)
+        const uint4 av = park[tid * G::CPR + (cc ^ (tid & G::SW))];
+        x[4 * cc + 0] = csub(barrett_mul_lazy(av.x, x[4 * cc + 0], c), c.neg2q);
+        x[4 * cc + 1] = csub(barrett_mul_lazy(av.y, x[4 * cc + 1], c), c.neg2q);
+        x[4 * cc + 2] = csub(barrett_mul_lazy(av.z, x[4 * cc + 2], c), c.neg2q);
+        x[4 * cc + 3] = csub(barrett_mul_lazy(av.w, x[4 * cc + 3], c), c.neg2q);
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        PassAddr ad;
+        if (pass == 0) {
+            ad = pass_addr<LOGN, LE>(twi, tid);
+        } else {
+            ad = pass_addr<LOGN, LE>(twic, 0u);
+            lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
+        }
+        gs_stages_down_to1<LOGN, LE, LE - 1>(x, ad, c);
+        if (pass == 0) {
+            if (G::LT == LE) gs_stage<LOGN, LE, 0>(x, ad, c);
+            sts_row<LOGN, LE>(sm, x, tid);           // own row of `sm`: last read by this thread (lds_row of b)
+            poly_sync<G::TPP>();
+        }
+    }
+    {
+        const uint2 wn = __ldg(twi), w1n = __ldg(twi + 1);
+#pragma unroll
+        for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
+    }
+#pragma unroll
+    for (int k = 0; k < G::E; k++) __stcs(out + off + tid + G::TPP * k, x[k]);
 }
 
 // ---------------------------------------------------------------------------------- generic (any n) u32 kernels

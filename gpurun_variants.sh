@@ -1,9 +1,11 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-AGX_LIB=$PWD/agilex-ntt_b200/lib/libagxntt_trace.so python profiles/trace_phases.py 2>&1 | tee gpurun_out/trace_phases.txt | head -3
-for v in "" _pf2; do
-  export AGX_LIB=$PWD/agilex-ntt_b200/lib/libagxntt$v.so
-  python bench.py --steps 20 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/bench$v.json 2>gpurun_out/bench$v.err
-  python -c "
-import json; d=json.load(open('gpurun_out/bench$v.json')); print('variant[$v] fwd_ms', d['kernels']['ntt_fwd_ms'], 'inv_ms', d['kernels']['ntt_inv_ms'])"
-done
+python profiles/bench_extra.py > gpurun_out/bench_extra.jsonl 2> gpurun_out/bench_extra.err
+python -c "
+import json
+for l in open('gpurun_out/bench_extra.jsonl'):
+    d=json.loads(l)
+    if d['kind']=='ntt': print('n=%d L=%d fwd %.3f ms (%.0f GB/s, %.2f)  inv %.3f ms (%.0f GB/s)  pairs/s %.1fM' % (d['n'], d['nlimbs'], d['fwd_ms'], d['fwd_GBps'], d['fwd_frac_of_measured_hbm'], d['inv_ms'], d['inv_GBps'], d['pairs_per_s']/1e6))
+    else: print('polymul n=%d B=%d %.3f ms  %.1fM products/s  %.0f GB/s' % (d['n'], d['batch'], d['ms'], d['products_per_s']/1e6, d['GBps']))
+"
+tail -2 gpurun_out/bench_extra.err
