@@ -91,6 +91,49 @@ __device__ __forceinline__ void prefetch_ahead(const uint32_t *g_this, uint32_t 
     }
 }
 
+
+// Streaming accesses to the polynomial rows: read once / written once per launch, so they must not displace the
+// twiddle table from L1 (AGX_STREAM_POLICY 0: ld/st.global.cs; 1: L1::no_allocate loads; experiments in profiles/).
+#ifndef AGX_STREAM_POLICY
+#define AGX_STREAM_POLICY 0
+#endif
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+#if AGX_STREAM_POLICY == 1
+    uint32_t v;
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+#if AGX_STREAM_POLICY == 1
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ uint2 ld_twiddle(const uint2 *p) {
+#if AGX_STREAM_POLICY == 1
+    uint2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint4 ld_twiddle(const uint4 *p) {
+#if AGX_STREAM_POLICY == 1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 template <int TPP>
 __device__ __forceinline__ void poly_sync() {
     if constexpr (TPP == 32) __syncwarp(); else __syncthreads();
@@ -156,7 +199,7 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
     const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
     uint4 v[G::N / 4 / G::TPP];
 #pragma unroll
-    for (int i = 0; i < G::N / 4 / G::TPP; i++) v[i] = __ldcs(g4 + i * G::TPP + tid);
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) v[i] = ld_stream(g4 + i * G::TPP + tid);
 #pragma unroll
     for (int i = 0; i < G::N / 4 / G::TPP; i++) {
         const uint32_t idx = i * G::TPP + tid, row = idx / G::CPR, c = idx % G::CPR;
@@ -205,11 +248,11 @@ template <int LOGN, int LE, int J>
 __device__ __forceinline__ void load_tw_generic(uint2 (&w)[1 << J], const PassAddr &a) {
     constexpr int LT = LOGN - LE, TPP = 1 << LT;
     if constexpr (J == 0) {
-        w[0] = __ldg(a.b2);
+        w[0] = ld_twiddle(a.b2);
     } else {
 #pragma unroll
         for (int h = 0; h < (1 << (J - 1)); h++) {
-            const uint4 v = __ldg(a.b4 + ((1 << (LT + J - 1)) + h * TPP));
+            const uint4 v = ld_twiddle(a.b4 + ((1 << (LT + J - 1)) + h * TPP));
             w[2 * h] = make_uint2(v.x, v.y);
             w[2 * h + 1] = make_uint2(v.z, v.w);
         }
@@ -275,7 +318,7 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
             for (int k = 0; k < G::E; k++) x[k] = tid * 977u + k * 131071u + poly;
 #else
 #pragma unroll
-            for (int k = 0; k < G::E; k++) x[k] = __ldcs(g + tid + G::TPP * k);
+            for (int k = 0; k < G::E; k++) x[k] = ld_stream(g + tid + G::TPP * k);
 #endif
             prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
         } else {                                     // row pass: x[j] = poly[E*tid + j], stages LE..logn-1
@@ -393,7 +436,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
             if (pass == 0) {
                 ad = pass_addr<LOGN, LE>(twfc, 0u);
 #pragma unroll
-                for (int k = 0; k < G::E; k++) x[k] = __ldcs(src + tid + G::TPP * k);
+                for (int k = 0; k < G::E; k++) x[k] = ld_stream(src + tid + G::TPP * k);
             } else {
                 ad = pass_addr<LOGN, LE>(twf, tid);
                 lds_row<LOGN, LE>(sm, x, tid);

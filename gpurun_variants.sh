@@ -1,11 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python profiles/bench_extra.py > gpurun_out/bench_extra.jsonl 2> gpurun_out/bench_extra.err
-python -c "
-import json
-for l in open('gpurun_out/bench_extra.jsonl'):
-    d=json.loads(l)
-    if d['kind']=='ntt': print('n=%d L=%d fwd %.3f ms (%.0f GB/s, %.2f)  inv %.3f ms (%.0f GB/s)  pairs/s %.1fM' % (d['n'], d['nlimbs'], d['fwd_ms'], d['fwd_GBps'], d['fwd_frac_of_measured_hbm'], d['inv_ms'], d['inv_GBps'], d['pairs_per_s']/1e6))
-    else: print('polymul n=%d B=%d %.3f ms  %.1fM products/s  %.0f GB/s' % (d['n'], d['batch'], d['ms'], d['products_per_s']/1e6, d['GBps']))
-"
-tail -2 gpurun_out/bench_extra.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_full.json 2>gpurun_out/bench_full.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2>gpurun_out/bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/bench_full.json; cat gpurun_out/bench_ref.json | cut -c1-300
