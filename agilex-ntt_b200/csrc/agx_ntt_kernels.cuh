@@ -48,6 +48,9 @@ struct KParams {
 #ifndef AGX_ABLATE
 #define AGX_ABLATE 0
 #endif
+#ifndef AGX_DIRECT_STORE
+#define AGX_DIRECT_STORE 0
+#endif
 #if AGX_TRACE
 #define AGX_STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x % 64) == 5) p.trace[(blockIdx.x / 64) * 16 + (i)] = clock64(); } while (0)
 #else
@@ -357,11 +360,19 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     for (int j = 0; j < G::E; j++) acc ^= x[j];
     if (acc == 0x12345678u) g[tid] = acc;            // ablation: keep the math alive, store (almost) nothing
 #else
+#if AGX_DIRECT_STORE
+    {   // experiment: rows straight from registers, 16 bytes per lane at a 4*E-byte stride (partial-sector writes)
+        uint4 *g4 = reinterpret_cast<uint4 *>(g) + tid * G::CPR;
+#pragma unroll
+        for (int cc = 0; cc < G::CPR; cc++) __stcs(g4 + cc, make_uint4(x[4 * cc], x[4 * cc + 1], x[4 * cc + 2], x[4 * cc + 3]));
+    }
+#else
     sts_row<LOGN, LE>(sm, x, tid);                   // own row only: no barrier needed before
     poly_sync<G::TPP>();
     AGX_STAMP(14);
     smem_to_global<LOGN, LE>(sm, g, tid);
     AGX_STAMP(15);
+#endif
 #endif
 }
 

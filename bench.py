@@ -36,6 +36,14 @@ SEED = 1234                         # timing seed
 HBM_FALLBACK_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def host_threads() -> int:
+    """All host threads this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -137,7 +145,7 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     sample = min(args.cpu_sample, 16384)            # per step; K steps of this stay within a couple of minutes
     P = O.Plan(args.n, [PRIME])
     x = P.synthetic(sample, seed=SEED)
@@ -193,6 +201,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -296,7 +306,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         if world == 1 and not args.no_cpu:
             from oracle import oracle as O
-            thr = O.max_threads()
+            thr = host_threads()
             sample = args.cpu_sample
             reps = 8                      # 262,144 pairs ~ 12 CPU-seconds of the Shoup-lazy port
             v, dt = cpu_pairs_per_sec(n, [PRIME], sample, reps, "shoup", thr)

@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_full.json 2>gpurun_out/bench_full.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2>gpurun_out/bench_ref.err; echo "ref rc=$?"
-cat gpurun_out/bench_full.json; cat gpurun_out/bench_ref.json | cut -c1-300
+for v in _ds; do
+  export AGX_LIB=$PWD/agilex-ntt_b200/lib/libagxntt$v.so
+  python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fwd_inv_vs_oracle" 2>&1 | tail -1
+  python bench.py --steps 20 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/bench$v.json 2>gpurun_out/bench$v.err
+  python -c "
+import json; d=json.load(open('gpurun_out/bench$v.json')); print('variant[$v] fwd_ms', d['kernels']['ntt_fwd_ms'], 'inv_ms', d['kernels']['ntt_inv_ms'], d['parity_in_bench'])"
+done
