@@ -63,9 +63,10 @@ struct Geo {
     static constexpr int E = 1 << LE;            // coefficients per thread
     static constexpr int LT = LOGN - LE;
     static constexpr int TPP = 1 << LT;          // threads per polynomial
-    static constexpr int CPR = E / 4;            // 16-byte chunks per smem row
-    static constexpr int SW = (CPR < 8 ? CPR : 8) - 1;
-    static constexpr int SMEM_BYTES = N * 4;
+    static constexpr int CPR = E / 4;            // 16-byte chunks of data per smem row
+    static constexpr int PITCH4 = CPR + 1;       // row pitch in 16-byte chunks: one chunk of padding per row
+    static constexpr int PITCH = 4 * PITCH4;     // ... in words
+    static constexpr int SMEM_CHUNKS = TPP * PITCH4;
     static_assert(LT >= 5 && LT <= LE, "need 32 <= TPP <= E");
 };
 
@@ -144,34 +145,39 @@ __device__ __forceinline__ void poly_sync() {
 
 // ---------------------------------------------------------------------------------------------- smem transposes
 
-// element e = tid + TPP*k lives at row e>>LE, column e&(E-1); 16-byte chunk index XOR-swizzled with row&SW.
+// Shared-memory image of one polynomial: TPP rows of E words, each row padded by 16 bytes (pitch 4E+16 bytes).
+// With that pitch every access pattern of the kernels is conflict-free AND a compile-time offset from a per-thread
+// base, so no address arithmetic is left in the unrolled code:
+//   columns (STS.32/LDS.32): element tid + TPP*k -> row*PITCH + col, lanes on consecutive words;
+//   rows (LDS.128/STS.128):  thread T, chunk c -> T*PITCH4 + c; eight consecutive T start 16 bytes apart mod 128;
+//   copy in/out (LDS.128/STS.128): chunk index i*TPP + tid -> consecutive chunks of one row per quarter-warp.
+// (An earlier XOR swizzle was also conflict-free but cost one LOP3 per access.)
 template <int LOGN, int LE>
-__device__ __forceinline__ uint32_t col_phys(uint32_t tid, int k) {
+__device__ __forceinline__ constexpr uint32_t col_off(int k) {
     using G = Geo<LOGN, LE>;
     const int ebase = G::TPP * k;
-    const int row = ebase >> LE;
-    const int colbase = ebase & (G::E - 1);
-    return row * G::E + ((colbase + tid) ^ ((row & G::SW) << 2));
+    return (ebase >> LE) * G::PITCH + (ebase & (G::E - 1));
 }
 
 template <int LOGN, int LE>
 __device__ __forceinline__ void sts_columns(uint32_t *sw, const uint32_t (&x)[1 << LE], uint32_t tid) {
 #pragma unroll
-    for (int k = 0; k < (1 << LE); k++) sw[col_phys<LOGN, LE>(tid, k)] = x[k];
+    for (int k = 0; k < (1 << LE); k++) sw[tid + col_off<LOGN, LE>(k)] = x[k];
 }
 
 template <int LOGN, int LE>
 __device__ __forceinline__ void lds_columns(const uint32_t *sw, uint32_t (&x)[1 << LE], uint32_t tid) {
 #pragma unroll
-    for (int k = 0; k < (1 << LE); k++) x[k] = sw[col_phys<LOGN, LE>(tid, k)];
+    for (int k = 0; k < (1 << LE); k++) x[k] = sw[tid + col_off<LOGN, LE>(k)];
 }
 
 template <int LOGN, int LE>
 __device__ __forceinline__ void lds_row(const uint4 *sm, uint32_t (&x)[1 << LE], uint32_t tid) {
     using G = Geo<LOGN, LE>;
+    const uint4 *r = sm + tid * G::PITCH4;
 #pragma unroll
     for (int c = 0; c < G::CPR; c++) {
-        const uint4 v = sm[tid * G::CPR + (c ^ (tid & G::SW))];
+        const uint4 v = r[c];
         x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
     }
 }
@@ -179,35 +185,32 @@ __device__ __forceinline__ void lds_row(const uint4 *sm, uint32_t (&x)[1 << LE],
 template <int LOGN, int LE>
 __device__ __forceinline__ void sts_row(uint4 *sm, const uint32_t (&x)[1 << LE], uint32_t tid) {
     using G = Geo<LOGN, LE>;
+    uint4 *r = sm + tid * G::PITCH4;
 #pragma unroll
-    for (int c = 0; c < G::CPR; c++)
-        sm[tid * G::CPR + (c ^ (tid & G::SW))] = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+    for (int c = 0; c < G::CPR; c++) r[c] = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
 }
 
-// coalesced 16-byte copies between the swizzled smem image and the polynomial's row in global memory
+// coalesced 16-byte copies between the padded smem image and the polynomial's row in global memory
 template <int LOGN, int LE>
 __device__ __forceinline__ void smem_to_global(const uint4 *sm, uint32_t *g, uint32_t tid) {
     using G = Geo<LOGN, LE>;
-    uint4 *g4 = reinterpret_cast<uint4 *>(g);
+    uint4 *g4 = reinterpret_cast<uint4 *>(g) + tid;
+    const uint4 *s = sm + (tid / G::CPR) * G::PITCH4 + (tid % G::CPR);
 #pragma unroll
-    for (int i = 0; i < G::N / 4 / G::TPP; i++) {
-        const uint32_t idx = i * G::TPP + tid, row = idx / G::CPR, c = idx % G::CPR;
-        __stcs(g4 + idx, sm[row * G::CPR + (c ^ (row & G::SW))]);
-    }
+    for (int i = 0; i < G::N / 4 / G::TPP; i++)      // chunk i*TPP + tid: row advances by TPP/CPR per step
+        __stcs(g4 + i * G::TPP, s[i * (G::TPP / G::CPR) * G::PITCH4]);
 }
 
 template <int LOGN, int LE>
 __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uint32_t tid) {
     using G = Geo<LOGN, LE>;
-    const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g) + tid;
+    uint4 *s = sm + (tid / G::CPR) * G::PITCH4 + (tid % G::CPR);
     uint4 v[G::N / 4 / G::TPP];
 #pragma unroll
-    for (int i = 0; i < G::N / 4 / G::TPP; i++) v[i] = ld_stream(g4 + i * G::TPP + tid);
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) v[i] = ld_stream(g4 + i * G::TPP);
 #pragma unroll
-    for (int i = 0; i < G::N / 4 / G::TPP; i++) {
-        const uint32_t idx = i * G::TPP + tid, row = idx / G::CPR, c = idx % G::CPR;
-        sm[row * G::CPR + (c ^ (row & G::SW))] = v[i];
-    }
+    for (int i = 0; i < G::N / 4 / G::TPP; i++) s[i * (G::TPP / G::CPR) * G::PITCH4] = v[i];
 }
 
 // minimum resident CTAs per SM requested from ptxas (sets the register cap): 64 coefficients/thread -> 512 threads
@@ -300,7 +303,7 @@ template <int LOGN, int LE>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
+    __shared__ uint4 sm[G::SMEM_CHUNKS];
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
@@ -380,7 +383,7 @@ template <int LOGN, int LE>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
+    __shared__ uint4 sm[G::SMEM_CHUNKS];
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
@@ -427,8 +430,8 @@ template <int LOGN, int LE>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, KParams p) {
     using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::N / 4];
-    __shared__ uint4 park[G::N / 4];
+    __shared__ uint4 sm[G::SMEM_CHUNKS];
+    __shared__ uint4 park[G::SMEM_CHUNKS];
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
@@ -466,7 +469,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
     }
 #pragma unroll
     for (int cc = 0; cc < G::CPR; cc++) {            // pointwise: NTT(a) .* NTT(b), lazily reduced to [0,2q)
-        const uint4 av = park[tid * G::CPR + (cc ^ (tid & G::SW))];
+        const uint4 av = park[tid * G::PITCH4 + cc];
         x[4 * cc + 0] = csub(barrett_mul_lazy(av.x, x[4 * cc + 0], c), c.neg2q);
         x[4 * cc + 1] = csub(barrett_mul_lazy(av.y, x[4 * cc + 1], c), c.neg2q);
         x[4 * cc + 2] = csub(barrett_mul_lazy(av.z, x[4 * cc + 2], c), c.neg2q);
