@@ -162,10 +162,31 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     using G = Geo<LOGN, LE>;
     const KParams p = kparams(c);
     const dim3 grid((unsigned)T), block(G::TPP);
-    if (op == OP_FWD) ntt_fwd_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, (uint32_t)T);
-    else if (op == OP_INV) ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, (uint32_t)T);
-    else polymul_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
-    c->launches++;
+    const uint32_t Tu = (uint32_t)T;
+    if (op == OP_FWD) {
+        ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(out, out, nullptr, p, Tu);
+        c->launches++;
+    } else if (op == OP_INV) {
+        ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, Tu);
+        c->launches++;
+    } else if (LOGN <= 10) {
+        // n = 1024: forward(a), forward(b), pointwise, inverse fused in one launch (its 28 KB of code fits the
+        // instruction cache; at n >= 2048 the fused kernel is 57-60 KB and runs 30 % slower than the split below)
+        polymul_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
+        c->launches++;
+    } else {
+        // three launches, no scratch buffer: out = NTT(a); out = NTT(b) .* out; out = INTT(out)
+        if (out == b && out != a) { const uint32_t *t = a; a = b; b = t; }     // the product commutes
+        ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(out, a, nullptr, p, Tu);
+        if (a == b) {                                                          // squaring: out already holds NTT(b)
+            const size_t total = T * G::N;
+            pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, LOGN, total);
+        } else {
+            ntt_fwd_loop_kernel<LOGN, LE, true><<<grid, block, 0, s>>>(out, b, out, p, Tu);
+        }
+        ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, Tu);
+        c->launches += 3;
+    }
     return (int)cudaGetLastError();
 }
 

@@ -299,9 +299,12 @@ __device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const
     if constexpr (J > 1) gs_stages_down_to1<LOGN, LE, J - 1>(x, a, c);
 }
 
-template <int LOGN, int LE>
+// dst may equal src (in place: agx_ntt_fwd).  MUL: the three-launch polynomial product's middle step -- the spectrum
+// is multiplied pointwise by `mul` (the other operand's spectrum, same layout; may equal dst) before it is stored,
+// and left in [0,2q), which is what the inverse kernel accepts.
+template <int LOGN, int LE, bool MUL>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
+ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
     __shared__ uint4 sm[G::SMEM_CHUNKS];
     const uint32_t tid = threadIdx.x;
@@ -310,7 +313,8 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     const LimbConst c = p.lc[limb];
     const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
     const uint2 *twc = p.twc_fwd + (size_t)limb * G::N;
-    uint32_t *g = data + (size_t)poly * G::N;
+    const uint32_t *gs = src + (size_t)poly * G::N;
+    uint32_t *g = dst + (size_t)poly * G::N;
 
     uint32_t x[G::E];
     AGX_STAMP(0);
@@ -324,9 +328,9 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
             for (int k = 0; k < G::E; k++) x[k] = tid * 977u + k * 131071u + poly;
 #else
 #pragma unroll
-            for (int k = 0; k < G::E; k++) x[k] = ld_stream(g + tid + G::TPP * k);
+            for (int k = 0; k < G::E; k++) x[k] = ld_stream(gs + tid + G::TPP * k);
 #endif
-            prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
+            prefetch_ahead<LOGN, G::TPP>(gs, poly, T, tid);
         } else {                                     // row pass: x[j] = poly[E*tid + j], stages LE..logn-1
             a = pass_addr<LOGN, LE>(tw, tid);
 #if !(AGX_ABLATE & 4)
@@ -357,6 +361,19 @@ ntt_fwd_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 #pragma unroll
     for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
 #endif
+    if constexpr (MUL) {
+        poly_sync<G::TPP>();                         // every thread has read its row of the transpose buffer
+        global_to_smem<LOGN, LE>(sm, mul + (size_t)poly * G::N, tid);
+        poly_sync<G::TPP>();
+#pragma unroll
+        for (int cc = 0; cc < G::CPR; cc++) {
+            const uint4 mv = sm[tid * G::PITCH4 + cc];
+            x[4 * cc + 0] = csub(barrett_mul_lazy(mv.x, x[4 * cc + 0], c), c.neg2q);
+            x[4 * cc + 1] = csub(barrett_mul_lazy(mv.y, x[4 * cc + 1], c), c.neg2q);
+            x[4 * cc + 2] = csub(barrett_mul_lazy(mv.z, x[4 * cc + 2], c), c.neg2q);
+            x[4 * cc + 3] = csub(barrett_mul_lazy(mv.w, x[4 * cc + 3], c), c.neg2q);
+        }
+    }
 #if AGX_ABLATE & 2
     uint32_t acc = 0;
 #pragma unroll
@@ -545,7 +562,7 @@ __global__ void __launch_bounds__(256) ntt_generic_kernel(uint32_t *__restrict__
 }
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(256) pointwise_generic_kernel(uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+__global__ void __launch_bounds__(256) pointwise_generic_kernel(uint32_t *a, const uint32_t *b,   // a may equal b (squaring)
                                                                 const LimbConst *__restrict__ lc, uint32_t L,
                                                                 uint32_t logn, size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

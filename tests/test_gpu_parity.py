@@ -222,9 +222,17 @@ def test_polymul_vs_oracle_and_schoolbook(A, torch, n):
         for l, q in enumerate(primes):
             assert (got[0, l] == O.polymul_schoolbook(a[0, l], b[0, l], q)).all()
         assert (to_np(da).reshape(a.shape) == a).all() and (to_np(db).reshape(a.shape) == b).all()
-        if n >= 1024:   # in place over a (the tuned kernel allows aliasing)
+        if n >= 1024:   # the tuned paths allow every aliasing: c == a, c == b, and squaring a == b (== c)
             c.polymul(da, da, db)
             assert (to_np(da).reshape(a.shape) == got).all()
+            da2 = to_dev(torch, a)
+            c.polymul(db, da2, db)
+            assert (to_np(db).reshape(a.shape) == got).all()
+            sq = P.polymul(a, a)
+            c.polymul(dc, da2, da2)
+            assert (to_np(dc).reshape(a.shape) == sq).all()
+            c.polymul(da2, da2, da2)
+            assert (to_np(da2).reshape(a.shape) == sq).all()
 
 
 def test_polymul_kat(A, torch):
