@@ -135,6 +135,30 @@ def cpu_pairs_per_sec(n: int, primes, sample_polys: int, reps: int, variant: str
     return sample_polys * len(primes) * reps / dt, dt
 
 
+def reference_code_rate():
+    """The reference's OWN kernel code (src/kernel/ntt.cpp compiled against the host SYCL stand-in, oracle/_ref), timed
+    on the one BASELINE size it supports (n=1024, forward only, u64, one host thread -- it is a sequential emulation
+    of the FPGA pipeline).  Returned as context next to the port's numbers; None where oracle/_ref was not built."""
+    try:
+        import numpy as np
+        from oracle import oracle as O
+        N, frames = 1024, 256
+        if not O.ref_available(N):
+            return None
+        tw, pre = O.tables_u64(N, PRIME)
+        x = (np.arange(N * frames, dtype=np.uint64) * np.uint64(2654435761)) % np.uint64(PRIME)
+        O.reference_fwd_u64(N, x, x, PRIME, tw, pre, frames)
+        t0 = time.perf_counter()
+        reps = 4
+        for _ in range(reps):
+            O.reference_fwd_u64(N, x, x, PRIME, tw, pre, frames)
+        dt = time.perf_counter() - t0
+        return {"what": "reference's own fwd_ntt_kernel code via oracle/_ref, n=1024 forward u64, 1 thread",
+                "forward_transforms_per_s": frames * reps / dt}
+    except Exception as e:       # never let the context number break the bench line
+        return {"error": repr(e)}
+
+
 def run_reference(args, rank: int):
     """--impl reference: the reference's CPU implementation of the path, on this box's host cores.
 
@@ -165,7 +189,8 @@ def run_reference(args, rank: int):
                                f"each step = bounded sample of {sample} polynomials of the 65,536-polynomial batch",
                    "n": args.n, "nlimbs": 1, "batch_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} fwd+inv pairs per step x {args.steps} steps, Shoup-lazy C oracle, OpenMP"},
+                         "sample": f"{sample} fwd+inv pairs per step x {args.steps} steps, Shoup-lazy C oracle, OpenMP",
+                         "reference_code": reference_code_rate()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -326,7 +351,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                     "sample": f"{sample} of the {B} polynomials x {reps} reps, fwd+inv, Shoup-lazy C "
                                               f"oracle (ntt.cpp:331-393 arithmetic at u32), OpenMP x{thr}; "
                                               f"{dt:.1f} s wall",
-                                    "barrett_value": vb, "single_core_value": v1}
+                                    "barrett_value": vb, "single_core_value": v1,
+                                    "reference_code": reference_code_rate()}
         print(json.dumps(line), flush=True)
         if bad != 0.0:
             raise SystemExit("bench.py: parity check inside the bench FAILED")
