@@ -2,6 +2,7 @@
 #include "../../include/agxntt.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -259,7 +260,12 @@ int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
             CK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
         }
         const size_t poly_bytes = (size_t)c->L * c->n * 4;
-        size_t polys = kChunkBytes / poly_bytes;
+        size_t chunk_bytes = kChunkBytes;
+        if (const char *e = getenv("AGX_HOST_CHUNK_MB")) {            // tuning knob for the host pipeline
+            const long mb = atol(e);
+            if (mb >= 1 && mb <= 1024) chunk_bytes = (size_t)mb << 20;
+        }
+        size_t polys = chunk_bytes / poly_bytes;
         if (polys == 0) polys = 1;
         P.cap = polys * poly_bytes;
         for (int i = 0; i < kSlots; i++) CK(cudaMalloc(&P.d_a[i], P.cap));

@@ -384,3 +384,43 @@ def test_config5_sizes_roundtrip_large(A, torch, n):
     assert (hi == P.fwd(P.synthetic(512, seed=1234, first_poly=B - 512))).all()
     c.inv(d)
     assert c.checksum(d) == chk
+
+
+# ------------------------------------------------------------------------------------- API behaviour on the GPU
+
+def test_two_contexts_two_streams(A, torch):
+    """No hidden global state: different (n, primes) contexts interleaved on different streams stay correct."""
+    c1, c2 = ctx_for(A, 4096, Q[:1]), ctx_for(A, 2048, Q)
+    P1, P2 = O.Plan(4096, Q[:1]), O.Plan(2048, Q)
+    x1, x2 = P1.synthetic(300, seed=5), P2.synthetic(200, seed=6)
+    d1, d2 = to_dev(torch, x1), to_dev(torch, x2)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        c1.fwd(d1, stream=s1); c2.fwd(d2, stream=s2)
+        c1.inv(d1, stream=s1); c2.inv(d2, stream=s2)
+    c1.fwd(d1, stream=s1); c2.fwd(d2, stream=s2)
+    torch.cuda.synchronize()
+    assert (to_np(d1).reshape(x1.shape) == P1.fwd(x1.copy(), threads=4)).all()
+    assert (to_np(d2).reshape(x2.shape) == P2.fwd(x2.copy(), threads=4)).all()
+
+
+def test_argument_errors(A, torch):
+    import ctypes
+    c = ctx_for(A, 4096, Q[:1])
+    L = A.lib()
+    assert L.agx_ntt_fwd(c._h, None, 4, None) == -1            # AGX_E_INVALID: null data with B > 0
+    assert L.agx_ntt_fwd(c._h, None, 0, None) == 0             # empty batch is fine
+    assert L.agx_polymul(c._h, ctypes.c_void_p(16), None, None, 1, None) == -1
+    assert L.agx_ntt_fwd_host(c._h, None, None, 3) == -1
+    assert L.agx_ntt_fwd_host(c._h, None, None, 0) == 0
+    assert L.agx_ntt_fwd(None, None, 0, None) == -1
+    v = ctypes.c_uint32()
+    assert L.agx_get_psi(c._h, 7, ctypes.byref(v)) == -1       # limb out of range
+    with pytest.raises(ValueError):
+        c.fwd(torch.zeros(4097, dtype=torch.int32, device="cuda"))      # not a whole number of polynomials
+    with pytest.raises(ValueError):
+        c.fwd(torch.zeros(4096, dtype=torch.int64, device="cuda"))      # wrong element size
+    p = A.RefPipeline()
+    assert L.agx_ntt_fwd(p._h, ctypes.c_void_p(16), 1, None) == -1      # table-less context: u32 calls refused
+    p.close()

@@ -75,3 +75,20 @@ def test_two_rank_shard_and_compare():
     assert (np.concatenate([ret["y0"], ret["y1"]]) == whole).all()
     assert ret["sum"] == O.checksum_u32(whole)
     assert ret["tmax"] == 2.0
+
+
+def test_shard_bounds_properties():
+    """Property test of the partition: disjoint cover, order-preserving, balanced."""
+    from hypothesis import given, settings, strategies as st
+    import agilex_ntt_b200 as A
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10**7), st.integers(1, 64))
+    def prop(B, w):
+        sh = A.all_shards(B, w)
+        assert sum(b - a for a, b in sh) == B
+        assert all(0 <= a <= b <= B for a, b in sh)
+        assert all(x[1] == y[0] for x, y in zip(sh, sh[1:]))
+        assert max(b - a for a, b in sh) - min(b - a for a, b in sh) <= 1
+    prop()
+    assert A.combine_checksums([2**64 - 1, 2]) == 1
