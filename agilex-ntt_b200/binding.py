@@ -42,6 +42,7 @@ def _load() -> C.CDLL:
         "agx_ntt_fwd": [vp, vp, C.c_size_t, vp],
         "agx_ntt_inv": [vp, vp, C.c_size_t, vp],
         "agx_polymul": [vp, vp, vp, vp, C.c_size_t, vp],
+        "agx_elementwise": [vp, C.c_int, vp, vp, vp, C.c_size_t, vp],
         "agx_ntt_fwd_host": [vp, vp, vp, C.c_size_t],
         "agx_ntt_inv_host": [vp, vp, vp, C.c_size_t],
         "agx_polymul_host": [vp, vp, vp, vp, C.c_size_t],
@@ -65,7 +66,7 @@ def _load() -> C.CDLL:
     return L
 
 
-EXPORTS = ("agx_create agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul "
+EXPORTS = ("agx_create agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise "
            "agx_ntt_fwd_host agx_ntt_inv_host agx_polymul_host agx_host_alloc agx_host_free agx_fill_synthetic "
            "agx_checksum agx_ref_input agx_ref_fwd agx_ref_output agx_wait agx_error_string agx_launch_count "
            "agx_variant").split()
@@ -169,6 +170,17 @@ class Context:
         if self._batch(b) != B or self._batch(c) != B:
             raise ValueError("shape mismatch")
         _ck(lib().agx_polymul(self._h, _dev_ptr(c), _dev_ptr(a), _dev_ptr(b), B, _stream_ptr(stream)), "agx_polymul")
+        return c
+
+    EW = {"add": 0, "sub": 1, "mul": 2, "mac": 3}
+
+    def elementwise(self, op: str, c, a, b, stream=None):
+        """c = a + b | a - b | a * b | c + a * b, modulo each limb's prime (operands reduced, device tensors)."""
+        B = self._batch(a)
+        if self._batch(b) != B or self._batch(c) != B:
+            raise ValueError("shape mismatch")
+        _ck(lib().agx_elementwise(self._h, self.EW[op], _dev_ptr(c), _dev_ptr(a), _dev_ptr(b), B, _stream_ptr(stream)),
+            "agx_elementwise")
         return c
 
     def fill_synthetic(self, t, seed: int = 42, first_poly: int = 0, stream=None):

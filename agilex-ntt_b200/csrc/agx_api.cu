@@ -469,6 +469,28 @@ int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db
     return launch(c, OP_MUL, dc, da, db, B, (cudaStream_t)stream);
 }
 
+int agx_elementwise(agx_ctx *c, int op, uint32_t *dc, const uint32_t *da, const uint32_t *db, size_t B, void *stream) {
+    int rc = check_dev_call(c, dc, B);
+    if (rc) return rc;
+    if (op < 0 || op > 3) return AGX_E_INVALID;
+    if (B == 0) return AGX_OK;
+    if (!da || !db) return AGX_E_INVALID;
+    const size_t total4 = B * c->L * c->n / 4;
+    size_t blocks = (total4 + 255) / 256;
+    if (blocks > (size_t)c->sms * 16) blocks = (size_t)c->sms * 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint4 *c4 = reinterpret_cast<uint4 *>(dc);
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(da), *b4 = reinterpret_cast<const uint4 *>(db);
+    switch (op) {
+        case EW_ADD: elementwise_kernel<EW_ADD><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
+        case EW_SUB: elementwise_kernel<EW_SUB><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
+        case EW_MUL: elementwise_kernel<EW_MUL><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
+        default:     elementwise_kernel<EW_MAC><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
+    }
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
 int agx_ntt_fwd_host(agx_ctx *c, const uint32_t *h_in, uint32_t *h_out, size_t B) {
     return run_host(c, OP_FWD, h_in, nullptr, h_out, B);
 }

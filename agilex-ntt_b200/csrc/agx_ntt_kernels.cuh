@@ -571,6 +571,38 @@ __global__ void __launch_bounds__(256) pointwise_generic_kernel(uint32_t *a, con
     a[i] = csub(barrett_mul_lazy(a[i], b[i], c), c.neg2q);   // [0,2q): valid inverse input
 }
 
+// ------------------------------------------------------------------- limb-wise (RNS) element-wise arithmetic
+// The operations a caller performs around the transforms on [B][L][n] data: add, subtract,
+// multiply and multiply-accumulate modulo each limb's prime, e.g. on spectra between agx_ntt_fwd and agx_ntt_inv.
+// Pure streaming kernels: 16-byte vector accesses, grid-stride, 3 (add/sub/mul) or 4 (mac) u32 streams of HBM traffic.
+enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2, EW_MAC = 3 };
+
+template <int OP>
+__device__ __forceinline__ uint32_t ew_apply(uint32_t cv, uint32_t av, uint32_t bv, const LimbConst &c) {
+    if (OP == EW_ADD) return csub(av + bv, c.negq);
+    if (OP == EW_SUB) return csub(av + c.q - bv, c.negq);
+    const uint32_t m = csub(csub(barrett_mul_lazy(av, bv, c), c.neg2q), c.negq);
+    if (OP == EW_MUL) return m;
+    return csub(cv + m, c.negq);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) elementwise_kernel(uint4 *c4, const uint4 *a4, const uint4 *b4,
+                                                          const LimbConst *__restrict__ lc, uint32_t L, uint32_t logn,
+                                                          size_t total4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const LimbConst c = lc[((i * 4) >> logn) % L];
+        const uint4 a = a4[i], b = b4[i];
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (OP == EW_MAC) r = c4[i];
+        r.x = ew_apply<OP>(r.x, a.x, b.x, c);
+        r.y = ew_apply<OP>(r.y, a.y, b.y, c);
+        r.z = ew_apply<OP>(r.z, a.z, b.z, c);
+        r.w = ew_apply<OP>(r.w, a.w, b.w, c);
+        c4[i] = r;
+    }
+}
+
 // ------------------------------------------------------------------------- reference-shaped u64 forward kernel
 // Arithmetic of fwd_ntt_kernel (ntt.cpp:146-159, 292-300, 331-332, 344-363, 368-369, 377-393), including
 // wrap-around mod 2^64 when the tables are not Shoup pairs (main.cpp:49-55 feeds such data).  One CTA per frame

@@ -75,6 +75,16 @@ int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
 /* c = a * b mod (X^n + 1, q_limb): forward(a), forward(b), pointwise, inverse in ONE launch. c may alias a or b. */
 int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
 
+/* ---- limb-wise element-wise arithmetic on [B][L][n] DEVICE data (the operations callers run around the transforms,
+ * e.g. spectrum multiply-accumulate between agx_ntt_fwd and agx_ntt_inv; no reference
+ * counterpart).  Operands must be reduced (< q_limb); results are in [0, q_limb).  d_c may alias d_a and/or d_b. ---- */
+#define AGX_EW_ADD 0 /* c = a + b     */
+#define AGX_EW_SUB 1 /* c = a - b     */
+#define AGX_EW_MUL 2 /* c = a * b     */
+#define AGX_EW_MAC 3 /* c = c + a * b */
+int agx_elementwise(agx_ctx *ctx, int op, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B,
+                    void *stream);
+
 /* ---- the same on HOST pointers: chunked H2D / kernel / D2H pipeline over the context's own streams.
  * Pinned memory (agx_host_alloc, cudaHostAlloc, cudaHostRegister) is copied directly; pageable memory is staged
  * through internal pinned buffers.  h_out may equal h_in. ---- */

@@ -424,3 +424,37 @@ def test_argument_errors(A, torch):
     p = A.RefPipeline()
     assert L.agx_ntt_fwd(p._h, ctypes.c_void_p(16), 1, None) == -1      # table-less context: u32 calls refused
     p.close()
+
+
+def test_elementwise_rns_ops(A, torch):
+    """add / sub / mul / mac modulo each limb's prime vs numpy, then the classic use: a spectrum-domain
+    multiply-accumulate equals the sum of two negacyclic products."""
+    n = 2048
+    c = ctx_for(A, n, Q)
+    P = O.Plan(n, Q)
+    B = 19
+    a, b, acc = P.synthetic(B, seed=1), P.synthetic(B, seed=2), P.synthetic(B, seed=3)
+    qv = np.array(Q, dtype=np.uint64).reshape(1, 3, 1)
+    da, db, dacc = to_dev(torch, a), to_dev(torch, b), to_dev(torch, acc)
+    out = torch.empty_like(da)
+    a64, b64, acc64 = a.astype(np.uint64), b.astype(np.uint64), acc.astype(np.uint64)
+    c.elementwise("add", out, da, db)
+    assert (to_np(out).reshape(a.shape) == (a64 + b64) % qv).all()
+    c.elementwise("sub", out, da, db)
+    assert (to_np(out).reshape(a.shape) == (a64 + qv - b64) % qv).all()
+    c.elementwise("mul", out, da, db)
+    assert (to_np(out).reshape(a.shape) == (a64 * b64) % qv).all()
+    c.elementwise("mac", dacc, da, db)
+    assert (to_np(dacc).reshape(a.shape) == (acc64 + a64 * b64) % qv).all()
+    c.elementwise("mul", da, da, da)                       # aliasing: in-place square
+    assert (to_np(da).reshape(a.shape) == (a64 * a64) % qv).all()
+    # a*b + a2*b2 through the spectrum domain
+    a2, b2 = P.synthetic(B, seed=4), P.synthetic(B, seed=5)
+    d = [to_dev(torch, v) for v in (a, b, a2, b2)]
+    for t in d:
+        c.fwd(t)
+    c.elementwise("mul", d[0], d[0], d[1])
+    c.elementwise("mac", d[0], d[2], d[3])
+    c.inv(d[0])
+    want = (P.polymul(a, b).astype(np.uint64) + P.polymul(a2, b2)) % qv
+    assert (to_np(d[0]).reshape(a.shape) == want).all()
