@@ -234,8 +234,8 @@ class Plan:
             raise ValueError("invalid parameters (need prime q < 2^30 with q = 1 mod 2n)")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_plan_destroy(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:      # _LIB is gone at interpreter shutdown
+            _LIB.orc_plan_destroy(self._h)
             self._h = None
 
     def _chk(self, data):

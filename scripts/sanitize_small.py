@@ -1,0 +1,40 @@
+"""Tiny end-to-end exercise of every kernel for compute-sanitizer runs (one tool per gpurun call):
+   compute-sanitizer --tool racecheck python scripts/sanitize_small.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import agilex_ntt_b200 as A
+from oracle import oracle as O
+
+Q = O.SEAL_PRIMES_30
+for n in (4096, 2048, 1024, 256):
+    ctx = A.Context(n, Q)
+    P = O.Plan(n, Q)
+    x = P.synthetic(3, seed=1)
+    d = torch.from_numpy(x.view(np.int32)).cuda()
+    ctx.fwd(d)
+    assert (d.cpu().numpy().view(np.uint32).reshape(x.shape) == P.fwd(x.copy())).all()
+    ctx.inv(d)
+    assert (d.cpu().numpy().view(np.uint32).reshape(x.shape) == x).all()
+    a, b = P.synthetic(3, seed=2), P.synthetic(3, seed=3)
+    da, db = torch.from_numpy(a.view(np.int32)).cuda(), torch.from_numpy(b.view(np.int32)).cuda()
+    dc = torch.empty_like(da)
+    ctx.polymul(dc, da, db)
+    assert (dc.cpu().numpy().view(np.uint32).reshape(a.shape) == P.polymul(a, b)).all()
+    ctx.elementwise("mac", dc, da, db)
+    ctx.close()
+p = A.RefPipeline()
+N, q = 1024, Q[0]
+tw, pre = O.tables_u64(N, q)
+xin = np.arange(2 * N, dtype=np.uint64)
+out = np.zeros(2 * N, dtype=np.uint64)
+p.ntt_input_kernel(xin, xin, np.array([q], dtype=np.uint64), tw, pre, 2)
+p.fwd_ntt_kernel(0)
+p.ntt_output_kernel(out, 2)
+p.wait()
+assert (out == O.ref_fwd_u64(xin, xin, q, tw, pre, 2)).all()
+p.close()
+print("sanitize_small ok")
