@@ -194,12 +194,6 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
 int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     const size_t smem = (size_t)c->n * 4;
     const unsigned threads = c->n / 2 < 256 ? (c->n / 2 < 32 ? 32 : c->n / 2) : 256;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CK(cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
-        CK(cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
-        attr_done = true;
-    }
     if (op == OP_FWD) {
         ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
         c->launches++;
@@ -319,7 +313,10 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
             CK(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
         }
         rc = launch(c, op, P.d_a[sl], P.d_a[sl], P.d_b[sl], cnt, P.stream[sl]);
-        if (rc) return rc;
+        if (rc) {                                        // do not return with copies still touching caller memory
+            for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(P.stream[k]);
+            return rc;
+        }
         uint32_t *dst = h_out + off;
         if (!pin_o) { pend[sl].dst = dst; pend[sl].bytes = bytes; dst = P.p_out[sl]; }
         CK(cudaMemcpyAsync(dst, P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
@@ -379,11 +376,6 @@ int ref_flush(agx_ctx *c) {
     while ((1u << logn) < R.N) logn++;
     const size_t smem = (size_t)R.N * 8;
     const int use_smem = smem <= (128u << 10);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CK(cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
-        attr_done = true;
-    }
     const unsigned threads = R.N / 2 < 1024 ? (R.N / 2 < 32 ? 32 : R.N / 2) : 1024;
     ref_fwd_u64_kernel<<<R.frames, threads, use_smem ? smem : 0, R.stream>>>(R.d_in, R.d_in2, R.d_out, R.d_tw, R.d_pre,
                                                                            modulus, logn, use_smem);
@@ -409,6 +401,14 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
     if (!c) return AGX_E_NOMEM;
     c->device = device;
     cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+    // kernels that take more than 48 KB of dynamic shared memory opt in per device (function attributes are
+    // per-context state, so this is repeated for every context rather than cached in a process-wide flag)
+    {
+        cudaError_t e = cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        if (e != cudaSuccess) { delete c; return (int)e; }
+    }
     if (parms) {
         if (!parms->q || parms->nlimbs == 0 || parms->nlimbs > 64 || parms->logn < 3 || parms->logn > 15 ||
             parms->n != (1u << parms->logn)) { delete c; return AGX_E_INVALID; }
