@@ -177,6 +177,63 @@ int run_icache(int sms, uint32_t *d_out, long long *d_cyc, unsigned *d_slot, cud
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-file pressure test: the NTT kernels' inner structure without any memory traffic.  Each thread keeps 64
+// coefficients in registers and runs passes of 6 stages (stage j pairs x[k] with x[k + (32 >> j)], as the kernels do).
+// TW = 1: one twiddle for everything (operand-reuse friendly); TW = 2: one twiddle per stage group, i.e. 2^j distinct
+// twiddles in stage j, held in registers -- the kernels' situation.  512 threads/SM at <= 128 registers = 4 warps per
+// scheduler, the kernels' occupancy.  Reports butterflies/clk/SM.
+template <int TW>
+__global__ void __launch_bounds__(512, 1) regfile_kernel(uint32_t *out, long long *cycles, uint32_t seed, agx::LimbConst lc, int reps) {
+    uint32_t x[64];
+    uint2 w[32];
+#pragma unroll
+    for (int i = 0; i < 64; i++) x[i] = seed * (i + 1) + threadIdx.x * 977u;
+#pragma unroll
+    for (int i = 0; i < 32; i++) w[i] = make_uint2((seed + i * 7919u) | 1u, seed * 3u + i * 104729u);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            const int half = 32 >> j;
+#pragma unroll
+            for (int g = 0; g < (1 << j); g++)
+#pragma unroll
+                for (int i = 0; i < half; i++)
+                    agx::ct_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], TW == 1 ? w[0] : w[g], lc);
+        }
+        if (TW == 2) {      // keep the twiddle registers live and varying without loads
+#pragma unroll
+            for (int i = 0; i < 32; i++) w[i].x += x[i] & 2u;
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int TW>
+int run_regfile(int sms, uint32_t *d_out, long long *d_cyc, const agx::LimbConst &lc, cudaStream_t s) {
+    const int reps = 64;
+    for (int thr = 128; thr <= 512; thr *= 2) {
+        regfile_kernel<TW><<<sms, thr, 0, s>>>(d_out, d_cyc, 777u, lc, reps);
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        std::vector<long long> cyc(sms);
+        CK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+        std::sort(cyc.begin(), cyc.end());
+        const double med = (double)cyc[sms / 2];
+        printf("{\"test\": \"regfile_64coeff\", \"twiddles\": \"%s\", \"warps_per_sched\": %d, \"butterflies_per_clk_per_sm\": %.3f}\n",
+               TW == 1 ? "one" : "per_group", thr / 128, (double)reps * 192.0 * thr / med);
+    }
+    return 0;
+}
+
 int main() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -208,6 +265,8 @@ int main() {
         if (run<T_BFLY_CT_FP64>(sms, d_out, d_cyc, lc, s, thr)) return 1;
         if (run<T_BFLY_CT_HYBRID>(sms, d_out, d_cyc, lc, s, thr)) return 1;
     }
+    if (run_regfile<1>(sms, d_out, d_cyc, lc, s)) return 1;
+    if (run_regfile<2>(sms, d_out, d_cyc, lc, s)) return 1;
     if (getenv("AGX_MB_SKIP_ICACHE")) return 0;
     unsigned *d_slot;
     CK(cudaMalloc(&d_slot, sizeof(unsigned) * 256));
