@@ -101,3 +101,35 @@ def test_protocol_errors(A):
     with pytest.raises(A.AgxError):
         p.ntt_output_kernel(out, 2)
     p.close()
+
+
+def _run_driver(name, *args):
+    import os
+    import subprocess
+    import agilex_ntt_b200 as pkg
+    exe = os.path.join(os.path.dirname(pkg.build.LIB), "..", "bin", name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{name} not built (agx_ref_main needs the reference tree at build time)")
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    return [l for l in r.stdout.splitlines() if l.strip().isdigit()]
+
+
+def test_reference_main_cpp_unmodified_runs_on_the_gpu():
+    """The reference's own src/main.cpp, compiled unmodified against agilex-ntt_b200/host/, prints the known answer."""
+    lines = _run_driver("agx_ref_main")
+    assert len(lines) == 16384
+    txt = "".join(l + "\n" for l in lines)
+    assert hashlib.sha256(txt.encode()).hexdigest() == "68db50a07a87d4e18387a721d88b42291198aba2f9e9138e2e52d45ad6537c5c"
+
+
+def test_compat_driver_real_ntt_instance():
+    """Our main.cpp-shaped driver on a real instance: q = 1053818881, N = 1024, ramp input, 2 frames."""
+    N, q, frames = 1024, O.SEAL_PRIMES_30[0], 2
+    lines = _run_driver("agx_main_compat", "--seal", str(N), str(frames))
+    got = np.array([int(l) for l in lines], dtype=np.uint64)
+    tw, pre = O.tables_u64(N, q)
+    x = np.arange(N * frames, dtype=np.uint64) % np.uint64(q)
+    assert (got == O.ref_fwd_u64(x, x, q, tw, pre, frames)).all()
+    dummy = _run_driver("agx_main_compat")          # main.cpp's dummy data by default
+    assert len(dummy) == 16384 and int(dummy[0]) == 15752083817248508221
