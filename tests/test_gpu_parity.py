@@ -476,3 +476,23 @@ def test_two_devices_one_process(A, torch):
                 c.fwd(d)
                 assert (to_np(d).reshape(x.shape) == want).all()
             c.close()
+
+
+def test_five_limbs_and_27bit_primes(A, torch):
+    """Limb counts that divide nothing, and smaller (27-bit) primes: the limb index is poly % L inside the kernels and
+    the Barrett constants depend on the bit length of q."""
+    five = (1053818881, 1054015489, 1054212097, 1055260673, 1056178177)      # SURVEY.md App. A candidates
+    small = (134012929, 134111233, 134176769)                                # 27-bit, 2-adicity 13 -> n <= 4096
+    for primes, n in ((five, 4096), (five, 2048), (small, 4096), (small, 1024)):
+        c = ctx_for(A, n, primes)
+        P = O.Plan(n, primes)
+        x, y = P.synthetic(7, seed=21), P.synthetic(7, seed=22)
+        d = to_dev(torch, x)
+        c.fwd(d)
+        assert (to_np(d).reshape(x.shape) == P.fwd(x.copy())).all()
+        c.inv(d)
+        assert (to_np(d).reshape(x.shape) == x).all()
+        dx, dy = to_dev(torch, x), to_dev(torch, y)
+        dz = torch.empty_like(dx)
+        c.polymul(dz, dx, dy)
+        assert (to_np(dz).reshape(x.shape) == P.polymul(x, y)).all()
