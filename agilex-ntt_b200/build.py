@@ -88,6 +88,14 @@ def build_tools(force: bool = False) -> dict[str, str]:
                   "-L", LIBDIR, "-lagxntt", "-Wl,-rpath,$ORIGIN/../lib"])
         if os.path.exists(ref_bin):
             out["ref_main"] = ref_bin
+        # the header and library from plain C99
+        c_src, c_bin = os.path.join(HOST, "c_example.c"), os.path.join(BINDIR, "agx_c_example")
+        if os.path.exists(c_src) and (force or _stale(c_bin, [c_src, lib, os.path.join(ROOT, "include", "agxntt.h")])):
+            cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+            _run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O2", "-I", os.path.join(ROOT, "include"),
+                  "-o", c_bin, c_src, "-L", LIBDIR, "-lagxntt", "-Wl,-rpath,$ORIGIN/../lib"])
+        if os.path.exists(c_bin):
+            out["c_example"] = c_bin
     return out
 
 

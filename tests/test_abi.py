@@ -70,3 +70,4 @@ def test_compat_driver_builds():
     import agilex_ntt_b200 as A
     tools = A.build.build_tools()
     assert os.path.exists(tools["main_compat"]) and os.path.exists(tools["microbench"])
+    assert os.path.exists(tools["c_example"])      # include/agxntt.h is valid, warning-free C99 (-Werror -pedantic)

@@ -133,3 +133,13 @@ def test_compat_driver_real_ntt_instance():
     assert (got == O.ref_fwd_u64(x, x, q, tw, pre, frames)).all()
     dummy = _run_driver("agx_main_compat")          # main.cpp's dummy data by default
     assert len(dummy) == 16384 and int(dummy[0]) == 15752083817248508221
+
+
+def test_c_abi_from_plain_c():
+    """host/c_example.c (C99, no CUDA headers): round trip and X^(n-1) * X = -1 through the host-pointer entry points."""
+    import os
+    import subprocess
+    import agilex_ntt_b200 as pkg
+    exe = os.path.join(os.path.dirname(pkg.build.LIB), "..", "bin", "agx_c_example")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "c_example ok" in r.stdout, r.stderr[-500:]
