@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "agx_ntt_kernels.cuh"
+#include "agx_ntt_pers.cuh"
 #include "agx_tables.h"
 
 using namespace agx;
@@ -52,6 +53,7 @@ struct agx_ctx {
     bool has_parms = false;
     uint32_t n = 0, logn = 0, L = 0;
     int le = 0;                                    // 0 = generic kernel
+    unsigned grid_fwd = 0, grid_inv = 0;           // persistent kernels: resident CTAs on this device (multiple of L)
     std::vector<uint32_t> q, psi;
     std::vector<NaturalTables> nat_fwd, nat_inv;
     uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural when le == 0)
@@ -158,17 +160,62 @@ KParams kparams(const agx_ctx *c) {
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
+// Persistent forward / inverse kernels (agx_ntt_pers.cuh) serve agx_ntt_fwd / agx_ntt_inv and the outer two launches
+// of the split polynomial product; AGX_PERSISTENT=0 builds the one-CTA-per-polynomial kernels instead (A/B runs).
+#ifndef AGX_PERSISTENT
+#define AGX_PERSISTENT 0
+#endif
+
+template <int LOGN, int LE>
+int setup_persistent(agx_ctx *c) {
+    using G = Geo<LOGN, LE>;
+    auto kf = ntt_fwd_pers_kernel<LOGN, LE>;
+    auto ki = ntt_inv_pers_kernel<LOGN, LE>;
+    // L1 must keep the row pass's per-thread twiddles (8n bytes per limb) resident: leave the carve-out to the driver
+    // unless told otherwise (AGX_CARVEOUT_FWD / AGX_CARVEOUT_INV = percent of the unified array used as shared memory)
+    if (const char *e = getenv("AGX_CARVEOUT_FWD")) CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    if (const char *e = getenv("AGX_CARVEOUT_INV")) CK(cudaFuncSetAttribute(ki, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    int of = 0, oi = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, kf, G::TPP, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oi, ki, G::TPP, 0));
+    if (of < 1 || oi < 1) return AGX_E_UNSUPPORTED;
+    if (const char *e = getenv("AGX_PERS_CTAS")) {                    // tuning knob: resident CTAs per SM
+        const int v = atoi(e);
+        if (v >= 1) { if (v < of) of = v; if (v < oi) oi = v; }
+    }
+    auto round_l = [&](int occ) {
+        unsigned g = (unsigned)occ * (unsigned)c->sms;
+        g -= g % c->L;
+        return g ? g : c->L;
+    };
+    c->grid_fwd = round_l(of);
+    c->grid_inv = round_l(oi);
+    return AGX_OK;
+}
+
 template <int LOGN, int LE>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     using G = Geo<LOGN, LE>;
     const KParams p = kparams(c);
     const dim3 grid((unsigned)T), block(G::TPP);
     const uint32_t Tu = (uint32_t)T;
+#if AGX_PERSISTENT
+#if AGX_PERS_SCHED
+    const dim3 gridf = grid, gridi = grid;         // one CTA index per polynomial; resident CTAs steal the pending ones
+#else
+    const dim3 gridf(Tu < c->grid_fwd ? Tu : c->grid_fwd), gridi(Tu < c->grid_inv ? Tu : c->grid_inv);   // T is a multiple of L
+#endif
+#define AGX_FWD(dst, src) ntt_fwd_pers_kernel<LOGN, LE><<<gridf, block, 0, s>>>(dst, src, p, Tu)
+#define AGX_INV(dst) ntt_inv_pers_kernel<LOGN, LE><<<gridi, block, 0, s>>>(dst, p, Tu)
+#else
+#define AGX_FWD(dst, src) ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu)
+#define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(dst, p, Tu)
+#endif
     if (op == OP_FWD) {
-        ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(out, out, nullptr, p, Tu);
+        AGX_FWD(out, out);
         c->launches++;
     } else if (op == OP_INV) {
-        ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, Tu);
+        AGX_INV(out);
         c->launches++;
     } else if (LOGN <= 10) {
         // n = 1024: forward(a), forward(b), pointwise, inverse fused in one launch (its 28 KB of code fits the
@@ -178,16 +225,18 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     } else {
         // three launches, no scratch buffer: out = NTT(a); out = NTT(b) .* out; out = INTT(out)
         if (out == b && out != a) { const uint32_t *t = a; a = b; b = t; }     // the product commutes
-        ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(out, a, nullptr, p, Tu);
+        AGX_FWD(out, a);
         if (a == b) {                                                          // squaring: out already holds NTT(b)
             const size_t total = T * G::N;
             pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, LOGN, total);
         } else {
             ntt_fwd_loop_kernel<LOGN, LE, true><<<grid, block, 0, s>>>(out, b, out, p, Tu);
         }
-        ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, p, Tu);
+        AGX_INV(out);
         c->launches += 3;
     }
+#undef AGX_FWD
+#undef AGX_INV
     return (int)cudaGetLastError();
 }
 
@@ -417,7 +466,10 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
         c->le = select_le(c->logn);
         c->q.assign(parms->q, parms->q + parms->nlimbs);
         c->psi.resize(c->L); c->nat_fwd.resize(c->L); c->nat_inv.resize(c->L);
-        const int rc = build_tables(c);
+        int rc = build_tables(c);
+#if AGX_PERSISTENT
+        if (!rc && c->le) rc = c->logn == 12 ? setup_persistent<12, 6>(c) : c->logn == 11 ? setup_persistent<11, 6>(c) : setup_persistent<10, 5>(c);
+#endif
         if (rc) { agx_destroy(c); return rc; }
     }
     *out = c;

@@ -119,6 +119,22 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     return __ldcs(p);
 #endif
 }
+// Result stores (AGX_STORE_POLICY 0: st.global.cs streaming; 1: default write-back; 2: .cg; 3: .wt; experiments in profiles/)
+#ifndef AGX_STORE_POLICY
+#define AGX_STORE_POLICY 0
+#endif
+template <typename V>
+__device__ __forceinline__ void st_stream(V *p, V v) {
+#if AGX_STORE_POLICY == 1
+    *p = v;
+#elif AGX_STORE_POLICY == 2
+    __stcg(p, v);
+#elif AGX_STORE_POLICY == 3
+    __stwt(p, v);
+#else
+    __stcs(p, v);
+#endif
+}
 __device__ __forceinline__ uint2 ld_twiddle(const uint2 *p) {
 #if AGX_STREAM_POLICY == 1
     uint2 v;
@@ -198,7 +214,7 @@ __device__ __forceinline__ void smem_to_global(const uint4 *sm, uint32_t *g, uin
     const uint4 *s = sm + (tid / G::CPR) * G::PITCH4 + (tid % G::CPR);
 #pragma unroll
     for (int i = 0; i < G::N / 4 / G::TPP; i++)      // chunk i*TPP + tid: row advances by TPP/CPR per step
-        __stcs(g4 + i * G::TPP, s[i * (G::TPP / G::CPR) * G::PITCH4]);
+        st_stream(g4 + i * G::TPP, s[i * (G::TPP / G::CPR) * G::PITCH4]);
 }
 
 template <int LOGN, int LE>
@@ -436,7 +452,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
         for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
     }
 #pragma unroll
-    for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
+    for (int k = 0; k < G::E; k++) st_stream(g + tid + G::TPP * k, x[k]);
 }
 
 // Fused negacyclic product c = a * b mod (X^n + 1, q): forward(a), forward(b), pointwise, inverse in ONE launch
@@ -514,7 +530,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
         for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
     }
 #pragma unroll
-    for (int k = 0; k < G::E; k++) __stcs(out + off + tid + G::TPP * k, x[k]);
+    for (int k = 0; k < G::E; k++) st_stream(out + off + tid + G::TPP * k, x[k]);
 }
 
 // ---------------------------------------------------------------------------------- generic (any n) u32 kernels
