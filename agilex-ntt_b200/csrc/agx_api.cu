@@ -34,15 +34,22 @@ struct HostPipe {
     bool have_b = false, have_stage = false;
 };
 
+constexpr size_t kRefChunkBytes = 16u << 20;       // frame data per slot of the reference-shaped pipeline
+
 struct RefState {
     bool have_in = false, have_fwd = false, have_out = false, busy = false;
     uint32_t N = 0, frames = 0;
     const uint64_t *in = nullptr, *in2 = nullptr, *mod = nullptr, *tw = nullptr, *pre = nullptr;
     uint64_t *out = nullptr;
     int32_t out_frames = 0;
-    uint64_t *d_in = nullptr, *d_in2 = nullptr, *d_out = nullptr, *d_tw = nullptr, *d_pre = nullptr;
-    size_t cap_data = 0, cap_tab = 0;
-    cudaStream_t stream = nullptr;
+    // device side: tables, and per slot one input and one output chunk (H2D / kernel / D2H of different slots overlap)
+    uint64_t *d_tw = nullptr, *d_pre = nullptr;
+    uint64_t *d_in[kSlots] = {}, *d_out[kSlots] = {};
+    uint64_t *p_in[kSlots] = {}, *p_out[kSlots] = {};      // pinned staging for pageable callers
+    size_t cap_chunk = 0, cap_tab = 0;
+    bool have_stage_in = false, have_stage_out = false;
+    cudaStream_t stream[kSlots] = {};
+    cudaEvent_t done[kSlots] = {}, tables = nullptr;
 };
 
 }  // namespace
@@ -55,8 +62,8 @@ struct agx_ctx {
     int le = 0;                                    // 0 = generic kernel
     unsigned grid_fwd = 0, grid_inv = 0;           // persistent kernels: resident CTAs on this device (multiple of L)
     std::vector<uint32_t> q, psi;
-    std::vector<NaturalTables> nat_fwd, nat_inv;
-    uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural when le == 0)
+    uint2 *d_nat_fwd = nullptr, *d_nat_inv = nullptr;      // natural order, ntt.cpp:298-300 (agx_get_tables)
+    uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural, with n^-1 in inverse entry 0, when le == 0)
     uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
     unsigned long long *d_sum = nullptr;
@@ -77,54 +84,21 @@ int select_le(uint32_t logn) {
     }
 }
 
-template <int LOGN, int LE>
-uint32_t kernel_pos(uint32_t k) {   // natural index k -> kernel-order index
-    constexpr int LT = LOGN - LE;
-    if (k < (1u << LE)) return k;
-    int s = 31 - __builtin_clz(k);
-    const uint32_t c = 1u << (s - LT), r = k - (1u << s);
-    return tw_pos<LOGN, LE>(s, r / c, r % c);
-}
-
-uint32_t kernel_pos_rt(uint32_t logn, int le, uint32_t k) {
-    if (le == 0) return k;
-    if (logn == 12) return kernel_pos<12, 6>(k);
-    if (logn == 11) return kernel_pos<11, 6>(k);
-    return kernel_pos<10, 5>(k);
-}
-
 int set_device(const agx_ctx *c) { CK(cudaSetDevice(c->device)); return AGX_OK; }
 
+// Per-limb scalars on the host (psi search, inverses, Barrett constants); the n-entry tables themselves are
+// computed on the device by gen_tables_kernel.
 int build_tables(agx_ctx *c) {
     const uint32_t n = c->n, L = c->L;
-    std::vector<uint2> hf((size_t)L * n), hi((size_t)L * n), cf((size_t)L * n, make_uint2(0, 0)), ci((size_t)L * n, make_uint2(0, 0));
-    const uint32_t lt = c->le ? c->logn - c->le : 0, tpp = 1u << lt;
+    const size_t entries = (size_t)L * n;
     std::vector<LimbConst> lc(L);
+    std::vector<LimbGen> lg(L);
     for (uint32_t l = 0; l < L; l++) {
         const uint32_t q = c->q[l];
         const uint32_t psi = minimal_psi(n, q);
         if (!psi) return AGX_E_INVALID;
         c->psi[l] = psi;
-        c->nat_fwd[l] = natural_tables(n, q, psi, false);
-        c->nat_inv[l] = natural_tables(n, q, psi, true);
-        const uint32_t ninv = (uint32_t)powmod_u64(n, q - 2, q);
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t pos = kernel_pos_rt(c->logn, c->le, k);
-            hf[(size_t)l * n + pos] = make_uint2(c->nat_fwd[l].w[k], c->nat_fwd[l].wp[k]);
-            uint32_t w = c->nat_inv[l].w[k];
-            if (k == 0) w = ninv;                                       // unused slot carries n^-1
-            if (k == 1 && c->le) w = (uint32_t)mulmod_u64(w, ninv, q);  // last GS stage folds n^-1 (two-pass kernels)
-            hi[(size_t)l * n + pos] = make_uint2(w, shoup_companion(w, q));
-        }
-        if (c->le) {   // column-pass tables: local stage j, pair h sits where the row pass of thread 0 looks
-            for (int j = 0; j < c->le; j++)
-                for (uint32_t g = 0; g < (1u << j); g++) {
-                    const uint32_t nat = (1u << j) + g;
-                    const uint32_t pos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (g >> 1) * tpp) + (g & 1);
-                    cf[(size_t)l * n + pos] = make_uint2(c->nat_fwd[l].w[nat], c->nat_fwd[l].wp[nat]);
-                    ci[(size_t)l * n + pos] = make_uint2(c->nat_inv[l].w[nat], c->nat_inv[l].wp[nat]);
-                }
-        }
+        lg[l] = LimbGen{q, psi, (uint32_t)powmod_u64(psi, q - 2, q), (uint32_t)powmod_u64(n, q - 2, q)};
         int k = 0;
         while ((1ull << k) <= q) k++;                                   // bit length of q
         LimbConst &x = lc[l];
@@ -134,24 +108,34 @@ int build_tables(agx_ctx *c) {
         x.bar_sh = (uint32_t)(k - 1);
         x.psi = psi; x.zero = 0;
     }
-    CK(cudaMalloc(&c->d_tw_fwd, hf.size() * sizeof(uint2)));
-    CK(cudaMalloc(&c->d_tw_inv, hi.size() * sizeof(uint2)));
+    LimbGen *d_lg = nullptr;
+    CK(cudaMalloc(&c->d_nat_fwd, entries * sizeof(uint2)));
+    CK(cudaMalloc(&c->d_nat_inv, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_lc, lc.size() * sizeof(LimbConst)));
     CK(cudaMalloc(&c->d_sum, sizeof(unsigned long long)));
 #if AGX_TRACE
     CK(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 16 * 4096));
     CK(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 16 * 4096));
 #endif
-    CK(cudaMemcpy(c->d_tw_fwd, hf.data(), hf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_tw_inv, hi.data(), hi.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_tw_fwd, entries * sizeof(uint2)));   // generic sizes: natural order with n^-1 in inverse entry 0
+    CK(cudaMalloc(&c->d_tw_inv, entries * sizeof(uint2)));
     if (c->le) {
-        CK(cudaMalloc(&c->d_twc_fwd, cf.size() * sizeof(uint2)));
-        CK(cudaMalloc(&c->d_twc_inv, ci.size() * sizeof(uint2)));
-        CK(cudaMemcpy(c->d_twc_fwd, cf.data(), cf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_twc_inv, ci.data(), ci.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_twc_fwd, entries * sizeof(uint2)));
+        CK(cudaMalloc(&c->d_twc_inv, entries * sizeof(uint2)));
+        CK(cudaMemset(c->d_twc_fwd, 0, entries * sizeof(uint2)));
+        CK(cudaMemset(c->d_twc_inv, 0, entries * sizeof(uint2)));
     }
-    return AGX_OK;
+    CK(cudaMalloc(&d_lg, lg.size() * sizeof(LimbGen)));
+    CK(cudaMemcpy(d_lg, lg.data(), lg.size() * sizeof(LimbGen), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
+    const unsigned total = 2u * L * n;
+    gen_tables_kernel<<<(total + 255) / 256, 256>>>(c->d_nat_fwd, c->d_nat_inv, c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd,
+                                                    c->d_twc_inv, d_lg, L, c->logn, c->le);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_lg);
+    return (int)e;
 }
 
 KParams kparams(const agx_ctx *c) {
@@ -393,6 +377,11 @@ void pipe_destroy(HostPipe &P) {
 
 // ------------------------------------------------------------------------------- reference-shaped u64 pipeline
 
+// Reference-shaped round: loader + compute unit + drain (ntt.cpp:508-607, 86-506, 610-640) as a chunked three-slot
+// pipeline.  Frame b takes its low half from in[b*N ..) and its high half from in2[b*N + N/2 ..) (ntt.cpp:582-591), so
+// only those halves cross PCIe (one contiguous copy when in2 == in, two pitched copies otherwise).  Pinned caller
+// buffers (the host mirror's sycl::buffer allocates pinned memory) are copied directly and the whole round is
+// asynchronous until agx_wait(); pageable buffers are staged through pinned chunks inside this call.
 int ref_flush(agx_ctx *c) {
     RefState &R = c->ref;
     if (!(R.have_in && R.have_fwd && R.have_out)) return AGX_OK;     // still waiting for the other calls
@@ -401,36 +390,106 @@ int ref_flush(agx_ctx *c) {
     if (R.frames == 0) return AGX_OK;
     int rc = set_device(c);
     if (rc) return rc;
-    if (!R.stream) CK(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
-    const size_t words = (size_t)R.N * R.frames;
-    if (words * 8 > R.cap_data) {
-        cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out);
-        R.d_in = R.d_in2 = R.d_out = nullptr; R.cap_data = 0;
-        CK(cudaMalloc(&R.d_in, words * 8)); CK(cudaMalloc(&R.d_in2, words * 8)); CK(cudaMalloc(&R.d_out, words * 8));
-        R.cap_data = words * 8;
+    if (!R.stream[0]) {
+        for (int i = 0; i < kSlots; i++) {
+            CK(cudaStreamCreateWithFlags(&R.stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&R.done[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&R.tables, cudaEventDisableTiming));
     }
-    if ((size_t)R.N * 8 > R.cap_tab) {
+    const size_t N = R.N, frame_bytes = N * 8, half_bytes = N * 4;
+    size_t chunk_frames = kRefChunkBytes / frame_bytes;
+    if (chunk_frames == 0) chunk_frames = 1;
+    if (chunk_frames > R.frames) chunk_frames = R.frames;
+    const size_t chunk_bytes = chunk_frames * frame_bytes;
+    if (chunk_bytes > R.cap_chunk) {
+        for (int i = 0; i < kSlots; i++) {
+            cudaFree(R.d_in[i]); cudaFree(R.d_out[i]);
+            if (R.p_in[i]) cudaFreeHost(R.p_in[i]);
+            if (R.p_out[i]) cudaFreeHost(R.p_out[i]);
+            R.d_in[i] = R.d_out[i] = R.p_in[i] = R.p_out[i] = nullptr;
+        }
+        R.cap_chunk = 0; R.have_stage_in = R.have_stage_out = false;
+        for (int i = 0; i < kSlots; i++) { CK(cudaMalloc(&R.d_in[i], chunk_bytes)); CK(cudaMalloc(&R.d_out[i], chunk_bytes)); }
+        R.cap_chunk = chunk_bytes;
+    }
+    if (frame_bytes > R.cap_tab) {
         cudaFree(R.d_tw); cudaFree(R.d_pre);
         R.d_tw = R.d_pre = nullptr; R.cap_tab = 0;
-        CK(cudaMalloc(&R.d_tw, (size_t)R.N * 8)); CK(cudaMalloc(&R.d_pre, (size_t)R.N * 8));
-        R.cap_tab = (size_t)R.N * 8;
+        CK(cudaMalloc(&R.d_tw, frame_bytes)); CK(cudaMalloc(&R.d_pre, frame_bytes));
+        R.cap_tab = frame_bytes;
+    }
+    const bool same = R.in2 == R.in;
+    const bool pin_in = is_pinned(R.in) && (same || is_pinned(R.in2)), pin_out = is_pinned(R.out);
+    if (!pin_in && !R.have_stage_in) {
+        for (int i = 0; i < kSlots; i++) CK(cudaHostAlloc(&R.p_in[i], R.cap_chunk, cudaHostAllocDefault));
+        R.have_stage_in = true;
+    }
+    if (!pin_out && !R.have_stage_out) {
+        for (int i = 0; i < kSlots; i++) CK(cudaHostAlloc(&R.p_out[i], R.cap_chunk, cudaHostAllocDefault));
+        R.have_stage_out = true;
     }
     const uint64_t modulus = R.mod[0];
-    CK(cudaMemcpyAsync(R.d_in, R.in, words * 8, cudaMemcpyHostToDevice, R.stream));
-    if (R.in2 == R.in) CK(cudaMemcpyAsync(R.d_in2, R.d_in, words * 8, cudaMemcpyDeviceToDevice, R.stream));
-    else CK(cudaMemcpyAsync(R.d_in2, R.in2, words * 8, cudaMemcpyHostToDevice, R.stream));
-    CK(cudaMemcpyAsync(R.d_tw, R.tw, (size_t)R.N * 8, cudaMemcpyHostToDevice, R.stream));
-    CK(cudaMemcpyAsync(R.d_pre, R.pre, (size_t)R.N * 8, cudaMemcpyHostToDevice, R.stream));
+    // tables: once per round (ntt.cpp:119-144 receives them once per mini-batch), the other slots wait for them
+    CK(cudaMemcpyAsync(R.d_tw, R.tw, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
+    CK(cudaMemcpyAsync(R.d_pre, R.pre, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
+    CK(cudaEventRecord(R.tables, R.stream[0]));
+    for (int i = 1; i < kSlots; i++) CK(cudaStreamWaitEvent(R.stream[i], R.tables, 0));
     uint32_t logn = 0;
     while ((1u << logn) < R.N) logn++;
-    const size_t smem = (size_t)R.N * 8;
-    const int use_smem = smem <= (128u << 10);
+    const int use_smem = frame_bytes <= (128u << 10);
     const unsigned threads = R.N / 2 < 1024 ? (R.N / 2 < 32 ? 32 : R.N / 2) : 1024;
-    ref_fwd_u64_kernel<<<R.frames, threads, use_smem ? smem : 0, R.stream>>>(R.d_in, R.d_in2, R.d_out, R.d_tw, R.d_pre,
-                                                                           modulus, logn, use_smem);
-    c->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(R.out, R.d_out, words * 8, cudaMemcpyDeviceToHost, R.stream));
+    struct Pending { uint64_t *dst; size_t bytes; };
+    Pending pend[kSlots] = {};
+    size_t done = 0;
+    for (size_t i = 0; done < R.frames; i++) {
+        const int sl = (int)(i % kSlots);
+        cudaStream_t st = R.stream[sl];
+        const size_t cnt = R.frames - done < chunk_frames ? R.frames - done : chunk_frames, bytes = cnt * frame_bytes;
+        const size_t off = done * N;
+        if (i >= (size_t)kSlots && (!pin_in || !pin_out)) {          // staging buffers of this slot are about to be reused
+            CK(cudaEventSynchronize(R.done[sl]));
+            if (pend[sl].dst) { memcpy(pend[sl].dst, R.p_out[sl], pend[sl].bytes); pend[sl].dst = nullptr; }
+        }
+        if (pin_in) {
+            if (same) {
+                CK(cudaMemcpyAsync(R.d_in[sl], R.in + off, bytes, cudaMemcpyHostToDevice, st));
+            } else {
+                CK(cudaMemcpy2DAsync(R.d_in[sl], frame_bytes, R.in + off, frame_bytes, half_bytes, cnt, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpy2DAsync(R.d_in[sl] + N / 2, frame_bytes, R.in2 + off + N / 2, frame_bytes, half_bytes, cnt,
+                                     cudaMemcpyHostToDevice, st));
+            }
+        } else {
+            if (same) {
+                memcpy(R.p_in[sl], R.in + off, bytes);
+            } else {
+                for (size_t f = 0; f < cnt; f++) {
+                    memcpy(R.p_in[sl] + f * N, R.in + off + f * N, half_bytes);
+                    memcpy(R.p_in[sl] + f * N + N / 2, R.in2 + off + f * N + N / 2, half_bytes);
+                }
+            }
+            CK(cudaMemcpyAsync(R.d_in[sl], R.p_in[sl], bytes, cudaMemcpyHostToDevice, st));
+        }
+        ref_fwd_u64_kernel<<<(unsigned)cnt, threads, use_smem ? frame_bytes : 0, st>>>(R.d_in[sl], R.d_in[sl], R.d_out[sl], R.d_tw,
+                                                                                    R.d_pre, modulus, logn, use_smem);
+        c->launches++;
+        rc = (int)cudaGetLastError();
+        if (rc) {
+            for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(R.stream[k]);
+            return rc;
+        }
+        uint64_t *dst = R.out + off;
+        if (!pin_out) { pend[sl].dst = dst; pend[sl].bytes = bytes; dst = R.p_out[sl]; }
+        CK(cudaMemcpyAsync(dst, R.d_out[sl], bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(R.done[sl], st));
+        done += cnt;
+    }
+    if (!pin_out) {                                                  // drain the staged results before returning
+        for (int sl = 0; sl < kSlots; sl++) {
+            CK(cudaStreamSynchronize(R.stream[sl]));
+            if (pend[sl].dst) memcpy(pend[sl].dst, R.p_out[sl], pend[sl].bytes);
+        }
+    }
     R.busy = true;
     return AGX_OK;
 }
@@ -465,7 +524,7 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
         c->n = parms->n; c->logn = parms->logn; c->L = parms->nlimbs;
         c->le = select_le(c->logn);
         c->q.assign(parms->q, parms->q + parms->nlimbs);
-        c->psi.resize(c->L); c->nat_fwd.resize(c->L); c->nat_inv.resize(c->L);
+        c->psi.resize(c->L);
         int rc = build_tables(c);
 #if AGX_PERSISTENT
         if (!rc && c->le) rc = c->logn == 12 ? setup_persistent<12, 6>(c) : c->logn == 11 ? setup_persistent<11, 6>(c) : setup_persistent<10, 5>(c);
@@ -482,9 +541,17 @@ int agx_destroy(agx_ctx *c) {
     cudaDeviceSynchronize();
     pipe_destroy(c->pipe);
     RefState &R = c->ref;
-    cudaFree(R.d_in); cudaFree(R.d_in2); cudaFree(R.d_out); cudaFree(R.d_tw); cudaFree(R.d_pre);
-    if (R.stream) cudaStreamDestroy(R.stream);
-    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
+    for (int i = 0; i < kSlots; i++) {
+        cudaFree(R.d_in[i]); cudaFree(R.d_out[i]);
+        if (R.p_in[i]) cudaFreeHost(R.p_in[i]);
+        if (R.p_out[i]) cudaFreeHost(R.p_out[i]);
+        if (R.stream[i]) cudaStreamDestroy(R.stream[i]);
+        if (R.done[i]) cudaEventDestroy(R.done[i]);
+    }
+    if (R.tables) cudaEventDestroy(R.tables);
+    cudaFree(R.d_tw); cudaFree(R.d_pre);
+    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_nat_fwd); cudaFree(c->d_nat_inv);
+    cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
     cudaFree(c->d_lc); cudaFree(c->d_sum); cudaFree(c->d_trace);
     delete c;
     return AGX_OK;
@@ -498,9 +565,11 @@ int agx_get_psi(const agx_ctx *c, uint32_t limb, uint32_t *psi) {
 
 int agx_get_tables(const agx_ctx *c, uint32_t limb, int inverse, uint32_t *roots, uint32_t *precons) {
     if (!c || !c->has_parms || limb >= c->L || !roots || !precons) return AGX_E_INVALID;
-    const NaturalTables &t = inverse ? c->nat_inv[limb] : c->nat_fwd[limb];
-    memcpy(roots, t.w.data(), (size_t)c->n * 4);
-    memcpy(precons, t.wp.data(), (size_t)c->n * 4);
+    CK(cudaSetDevice(c->device));
+    std::vector<uint2> t(c->n);
+    CK(cudaMemcpy(t.data(), (inverse ? c->d_nat_inv : c->d_nat_fwd) + (size_t)limb * c->n, (size_t)c->n * sizeof(uint2),
+                  cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < c->n; k++) { roots[k] = t[k].x; precons[k] = t[k].y; }
     return AGX_OK;
 }
 
@@ -631,7 +700,7 @@ int agx_wait(agx_ctx *c) {
     }
     if (R.busy) {
         CK(cudaSetDevice(c->device));
-        CK(cudaStreamSynchronize(R.stream));
+        for (int i = 0; i < kSlots; i++) CK(cudaStreamSynchronize(R.stream[i]));
         R.busy = false;
     }
     return AGX_OK;

@@ -662,6 +662,61 @@ __global__ void __launch_bounds__(1024) ref_fwd_u64_kernel(const uint64_t *__res
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = X[i];
 }
 
+// ------------------------------------------------------------------------------------- twiddle tables on device
+// The step before the path: the reference fills its root / precon buffers on the host (main.cpp:46-55) and the loader
+// broadcasts them (ntt.cpp:544-571).  Here one thread per (limb, direction, k) computes
+//   w = base^bitrev(k) mod q   (base = psi forward, psi^-1 inverse; the table order ntt.cpp:298-300 consumes),
+//   w' = floor(w * 2^32 / q)   (Shoup companion),
+// and writes it to the natural-order table (introspection, generic kernel), to its kernel-order slot (tw_pos) and, for
+// k < E, to the column pass's slot.  Inverse kernel-order entries 0 and 1 carry n^-1 (see ntt_inv_loop_kernel).
+struct LimbGen {
+    uint32_t q, psi, psi_inv, n_inv;
+};
+
+__device__ __forceinline__ uint32_t mulmod_dev(uint32_t a, uint32_t b, uint32_t q) {
+    return (uint32_t)(((uint64_t)a * b) % q);
+}
+
+// le == 0: generic sizes, kernel order == natural order and no column tables
+__global__ void __launch_bounds__(256) gen_tables_kernel(uint2 *__restrict__ nat_fwd, uint2 *__restrict__ nat_inv,
+                                                         uint2 *__restrict__ tw_fwd, uint2 *__restrict__ tw_inv,
+                                                         uint2 *__restrict__ twc_fwd, uint2 *__restrict__ twc_inv,
+                                                         const LimbGen *__restrict__ lg, uint32_t L, uint32_t logn, int le) {
+    const uint32_t n = 1u << logn;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 2u * L * n) return;
+    const uint32_t k = gid & (n - 1), limb = (gid >> logn) % L;
+    const bool inverse = gid >= L * n;
+    const LimbGen g = lg[limb];
+    const uint32_t e = __brev(k) >> (32 - logn);
+    uint32_t r = 1, b = inverse ? g.psi_inv : g.psi;
+    for (uint32_t i = 0; i < logn; i++) {
+        if ((e >> i) & 1) r = mulmod_dev(r, b, g.q);
+        b = mulmod_dev(b, b, g.q);
+    }
+    const size_t base = (size_t)limb * n;
+    const uint2 natural = make_uint2(r, (uint32_t)(((uint64_t)r << 32) / g.q));
+    (inverse ? nat_inv : nat_fwd)[base + k] = natural;
+    uint32_t w = r;
+    if (inverse && k == 0) w = g.n_inv;                                  // unused slot carries n^-1
+    if (inverse && k == 1 && le) w = mulmod_dev(r, g.n_inv, g.q);        // last GS stage folds n^-1 (two-pass kernels)
+    const uint2 entry = make_uint2(w, (uint32_t)(((uint64_t)w << 32) / g.q));
+    uint32_t pos = k;
+    if (le && k >= (1u << le)) {
+        const int s = 31 - __clz(k), lt = (int)logn - le;
+        const uint32_t c = 1u << (s - lt), rr = k - (1u << s), tpp = 1u << lt;
+        const uint32_t T = rr / c, kk = rr % c;
+        pos = c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * tpp + T) * 2 + (kk & 1);   // = tw_pos<LOGN,LE>(s, T, kk)
+    }
+    (inverse ? tw_inv : tw_fwd)[base + pos] = entry;
+    if (le && k >= 1 && k < (1u << le)) {   // column pass: local stage j, group gq sits where the row pass of thread 0 looks
+        const int j = 31 - __clz(k), lt = (int)logn - le;
+        const uint32_t gq = k - (1u << j), tpp = 1u << lt;
+        const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
+        (inverse ? twc_inv : twc_fwd)[base + cpos] = natural;
+    }
+}
+
 // ---------------------------------------------------------------------------------- synthetic data + checksum
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;

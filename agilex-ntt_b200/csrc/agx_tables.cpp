@@ -64,23 +64,4 @@ uint32_t minimal_psi(uint32_t n, uint32_t q) {
     return (uint32_t)best;
 }
 
-uint32_t shoup_companion(uint32_t w, uint32_t q) { return (uint32_t)(((uint64_t)w << 32) / q); }
-
-NaturalTables natural_tables(uint32_t n, uint32_t q, uint32_t psi, bool inverse) {
-    uint32_t logn = 0;
-    while ((1u << logn) < n) logn++;
-    const uint64_t base = inverse ? powmod_u64(psi, q - 2, q) : psi;
-    std::vector<uint32_t> pw(n);
-    uint64_t cur = 1;
-    for (uint32_t i = 0; i < n; i++) { pw[i] = (uint32_t)cur; cur = mulmod_u64(cur, base, q); }
-    NaturalTables t;
-    t.w.resize(n);
-    t.wp.resize(n);
-    for (uint32_t k = 0; k < n; k++) {
-        t.w[k] = pw[bit_reverse(k, logn)];
-        t.wp[k] = shoup_companion(t.w[k], q);
-    }
-    return t;
-}
-
 }  // namespace agx

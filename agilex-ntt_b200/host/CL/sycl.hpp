@@ -3,12 +3,13 @@
 //
 // Only the surface main.cpp touches is provided: buffer<T,1>(size), host_accessor(buf, write_only|read_only),
 // queue(selector, async_handler), queue::wait().  A `queue` owns one agx_ctx (include/agxntt.h); buffers are
-// plain host memory that the reference-named entry points hand to agx_ref_*.  As in SYCL, constructing a
+// page-locked host memory that the reference-named entry points hand to agx_ref_*.  As in SYCL, constructing a
 // host_accessor on a buffer with work in flight synchronises first, so main.cpp:80 is safe even without q.wait().
 // SYCL errors surface as C++ exceptions (the reference's entry points return void): sycl::exception here.
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -55,10 +56,28 @@ public:
 };
 
 namespace detail {
+// Buffer storage is page-locked host memory (agx_host_alloc) so that the loader and drain of the reference-shaped
+// pipeline DMA straight from / into it and a whole round stays asynchronous until queue::wait(); if pinning fails
+// (no device yet, limit reached) it falls back to ordinary memory, which the library stages through pinned chunks.
 template <typename T> struct buffer_state {
-    std::vector<T> data;
+    T* data = nullptr;
+    size_t count = 0;
+    bool pinned = false;
     std::unique_ptr<queue> pending;   // queue with work that reads/writes this buffer
+    explicit buffer_state(size_t n) : count(n) {
+        void* p = nullptr;
+        if (n && agx_host_alloc(&p, n * sizeof(T)) == AGX_OK && p) { data = static_cast<T*>(p); pinned = true; }
+        else data = static_cast<T*>(::operator new(n ? n * sizeof(T) : 1));
+        std::memset(static_cast<void*>(data), 0, n * sizeof(T));
+    }
+    buffer_state(const buffer_state&) = delete;
+    buffer_state& operator=(const buffer_state&) = delete;
+    ~buffer_state() {
+        sync_noexcept();
+        if (pinned) agx_host_free(data); else ::operator delete(data);
+    }
     void sync() { if (pending) { auto q = std::move(pending); q->wait(); } }
+    void sync_noexcept() { try { sync(); } catch (...) {} }
 };
 }  // namespace detail
 
@@ -66,10 +85,11 @@ template <typename T, int D = 1> class buffer {
     static_assert(D == 1, "only 1-D buffers are needed by the NTT kernel API");
     std::shared_ptr<detail::buffer_state<T>> st_;
 public:
-    explicit buffer(size_t n) : st_(std::make_shared<detail::buffer_state<T>>()) { st_->data.resize(n); }
-    size_t size() const { return st_->data.size(); }
+    explicit buffer(size_t n) : st_(std::make_shared<detail::buffer_state<T>>(n)) {}
+    size_t size() const { return st_->count; }
     size_t get_count() const { return size(); }
-    T* host_data() { return st_->data.data(); }
+    T* host_data() { return st_->data; }
+    bool is_pinned() const { return st_->pinned; }
     void mark_pending(const queue& q) { st_->pending.reset(new queue(q)); }
     void sync() { st_->sync(); }
 };

@@ -143,3 +143,45 @@ def test_c_abi_from_plain_c():
     exe = os.path.join(os.path.dirname(pkg.build.LIB), "..", "bin", "agx_c_example")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "c_example ok" in r.stdout, r.stderr[-500:]
+
+
+def _pinned_u64(a: np.ndarray) -> np.ndarray:
+    import torch
+    t = torch.empty(a.size, dtype=torch.int64).pin_memory()
+    v = t.numpy().view(np.uint64)
+    v[:] = a
+    v_holder.append(t)             # keep the page-locked allocation alive for the duration of the test
+    return v
+
+
+v_holder = []
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("same", [True, False])
+def test_chunked_pipeline_many_frames(A, pinned, same):
+    """More frames than one pipeline chunk holds (3 slots x 16 MiB): H2D / kernel / D2H overlap across slots; the high
+    halves come from in2 (ntt.cpp:582-591), by pitched copies when the caller's buffers are page-locked."""
+    N, q = 8192, O.SEAL_PRIMES_30[2]
+    frames = 4 * (16 << 20) // (N * 8) + 5          # 4 full chunks and a ragged one
+    tw, pre = O.tables_u64(N, q)
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 4 * q, size=N * frames, dtype=np.uint64)
+    x2 = x if same else rng.integers(0, q, size=N * frames, dtype=np.uint64)
+    want = O.ref_fwd_u64(x, x2, q, tw, pre, frames)
+    if pinned:
+        px = _pinned_u64(x)
+        px2 = px if same else _pinned_u64(x2)
+        p = A.RefPipeline()
+        out = _pinned_u64(np.zeros(N * frames, dtype=np.uint64))
+        p.ntt_input_kernel(px, px2, np.array([q], dtype=np.uint64), tw, pre, frames)
+        p.fwd_ntt_kernel(0)
+        p.ntt_output_kernel(out, frames)
+        p.wait()
+        assert p.launch_count() == 5
+        p.close()
+    else:
+        out, launches = run_pipeline(A, x, x2, q, tw, pre, frames)
+        assert launches == 5
+    assert (out == want).all()
+    v_holder.clear()
