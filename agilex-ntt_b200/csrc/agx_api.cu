@@ -470,9 +470,28 @@ int ref_flush(agx_ctx *c) {
             }
             CK(cudaMemcpyAsync(R.d_in[sl], R.p_in[sl], bytes, cudaMemcpyHostToDevice, st));
         }
-        ref_fwd_u64_kernel<<<(unsigned)cnt, threads, use_smem ? frame_bytes : 0, st>>>(R.d_in[sl], R.d_in[sl], R.d_out[sl], R.d_tw,
-                                                                                    R.d_pre, modulus, logn, use_smem);
-        c->launches++;
+        static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knob: one-CTA-per-frame radix-2 kernel
+        if (logn >= 10 && !naive) {
+            // register-radix passes over the L2-resident chunk: logN - 4 strided stages in groups of <= 4, then the
+            // last 4 stages on contiguous 16-coefficient runs (with the final reduction)
+            uint32_t s0 = 0, left = logn - 4, passes = (logn - 4 + 3) / 4;   // 11 -> 4,4,3; 10 -> 4,3,3; 9 -> 3,3,3; 6 -> 3,3
+            const uint64_t *src = R.d_in[sl];
+            for (; passes; passes--) {
+                const uint32_t ls = (left + passes - 1) / passes;
+                const unsigned blocks = (unsigned)((cnt << (logn - ls)) + 255) / 256;
+                if (ls == 4) ref_u64_strided_pass_kernel<4><<<blocks, 256, 0, st>>>(src, R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, s0, (uint32_t)cnt);
+                else         ref_u64_strided_pass_kernel<3><<<blocks, 256, 0, st>>>(src, R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, s0, (uint32_t)cnt);
+                c->launches++;
+                src = R.d_out[sl];
+                s0 += ls; left -= ls;
+            }
+            ref_u64_last_pass_kernel<<<(unsigned)((cnt << (logn - 4)) + 127) / 128, 128, 0, st>>>(R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, (uint32_t)cnt);
+            c->launches++;
+        } else {
+            ref_fwd_u64_kernel<<<(unsigned)cnt, threads, use_smem ? frame_bytes : 0, st>>>(R.d_in[sl], R.d_in[sl], R.d_out[sl], R.d_tw,
+                                                                                        R.d_pre, modulus, logn, use_smem);
+            c->launches++;
+        }
         rc = (int)cudaGetLastError();
         if (rc) {
             for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(R.stream[k]);

@@ -662,6 +662,110 @@ __global__ void __launch_bounds__(1024) ref_fwd_u64_kernel(const uint64_t *__res
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = X[i];
 }
 
+// ------------------------------------------------------------- reference-shaped u64 forward: register-radix passes
+// The reference's native sizes (ntt.h:11-20: 1024, 8192, 16384, 32768) as a sequence of launches over a chunk of
+// frames that stays resident in L2: every pass keeps 2^LS coefficients of one butterfly network in registers and
+// runs LS stages on them (ntt.cpp:146-159 loop nest, :292-300 twiddle index m + i, :331-369 butterfly), so a frame
+// makes logN/4 round trips instead of logN through shared memory, and N = 32768 (256 KB, more than an SM's shared
+// memory) needs no special case.  Arithmetic is the u64 butterfly of ref_fwd_u64_kernel, mod 2^64 exactly.
+//   strided passes : thread holds p = p_hi * 2^(logN-s0) + k * 2^(logN-s0-LS) + p_lo, k < 2^LS; consecutive threads
+//                    take consecutive p_lo (coalesced 8-byte accesses); twiddles are uniform over p_lo.
+//   last pass      : the final 4 stages act on 16 consecutive coefficients (128 B) per thread; a warp stages its
+//                    512 consecutive coefficients through a private padded shared-memory tile so that global
+//                    accesses stay coalesced; includes the final reduction to [0,q) (ntt.cpp:377-393).
+__device__ __forceinline__ void ref_bfly_u64(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twice) {
+    uint64_t tx = x;
+    if (tx >= twice) tx -= twice;                 // ntt.cpp:331-332
+    const uint64_t c1 = __umul64hi(y, Wp);        // ntt.cpp:344-358
+    const uint64_t Q = W * y - c1 * q;            // ntt.cpp:363
+    x = tx + Q;                                   // ntt.cpp:368
+    y = tx + twice - Q;                           // ntt.cpp:369
+}
+
+template <int LS>
+__device__ __forceinline__ void ref_stages_u64(uint64_t (&x)[1 << LS], const uint64_t *__restrict__ roots,
+                                               const uint64_t *__restrict__ precons, uint32_t s0, uint32_t p_hi, uint64_t q) {
+    const uint64_t twice = q << 1;
+#pragma unroll
+    for (int j = 0; j < LS; j++) {
+        constexpr int E = 1 << LS;
+        const int half = E >> (j + 1);
+        const uint32_t tbase = (1u << (s0 + j)) + (p_hi << j);      // roots[m + i]: m = 2^s groups, i = p >> (logN - s)
+#pragma unroll
+        for (int g = 0; g < (1 << j); g++) {
+            const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
+#pragma unroll
+            for (int i = 0; i < half; i++) ref_bfly_u64(x[g * 2 * half + i], x[g * 2 * half + i + half], W, Wp, q, twice);
+        }
+    }
+}
+
+template <int LS>
+__global__ void __launch_bounds__(256) ref_u64_strided_pass_kernel(const uint64_t *src, uint64_t *dst,
+                                                                   const uint64_t *__restrict__ roots,
+                                                                   const uint64_t *__restrict__ precons, uint64_t q,
+                                                                   uint32_t logn, uint32_t s0, uint32_t frames) {
+    constexpr int E = 1 << LS;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t frame = gid >> (logn - LS), tidx = gid & ((1u << (logn - LS)) - 1);
+    if (frame >= frames) return;
+    const uint32_t lo_bits = logn - s0 - LS;
+    const uint32_t p_lo = tidx & ((1u << lo_bits) - 1), p_hi = tidx >> lo_bits;
+    const size_t base = ((size_t)frame << logn) + ((size_t)p_hi << (logn - s0)) + p_lo;
+    uint64_t x[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) x[k] = src[base + ((size_t)k << lo_bits)];
+    ref_stages_u64<LS>(x, roots, precons, s0, p_hi, q);
+#pragma unroll
+    for (int k = 0; k < E; k++) dst[base + ((size_t)k << lo_bits)] = x[k];
+}
+
+__global__ void __launch_bounds__(128) ref_u64_last_pass_kernel(uint64_t *data, const uint64_t *__restrict__ roots,
+                                                                const uint64_t *__restrict__ precons, uint64_t q,
+                                                                uint32_t logn, uint32_t frames) {
+    constexpr int LS = 4, E = 16, PITCH4 = 9;                 // 8 chunks of 16 bytes per thread row + 1 of padding
+    __shared__ uint4 tile[4][32 * PITCH4];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t frame = gid >> (logn - LS), tidx = gid & ((1u << (logn - LS)) - 1);
+    if (frame >= frames) return;                              // whole warps: a frame has N/16 >= 64 threads
+    uint4 *t = tile[wib];
+    uint4 *g4 = reinterpret_cast<uint4 *>(data + ((size_t)(gid - lane) << LS));   // the warp's 512 coefficients
+#pragma unroll
+    for (int i = 0; i < 8; i++) {                             // chunk c = i*32 + lane: row c/8, column c%8
+        const uint32_t c = i * 32 + lane;
+        t[(c >> 3) * PITCH4 + (c & 7)] = g4[c];
+    }
+    __syncwarp();
+    uint64_t x[E];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 v = t[lane * PITCH4 + c];
+        x[2 * c] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+        x[2 * c + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    }
+    ref_stages_u64<LS>(x, roots, precons, logn - LS, tidx, q);
+    const uint64_t twice = q << 1;
+#pragma unroll
+    for (int k = 0; k < E; k++) {                             // ntt.cpp:377-393
+        uint64_t v = x[k];
+        if (v >= twice) v -= twice;
+        if (v >= q) v -= q;
+        x[k] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        t[lane * PITCH4 + c] = make_uint4((uint32_t)x[2 * c], (uint32_t)(x[2 * c] >> 32), (uint32_t)x[2 * c + 1],
+                                          (uint32_t)(x[2 * c + 1] >> 32));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t c = i * 32 + lane;
+        g4[c] = t[(c >> 3) * PITCH4 + (c & 7)];
+    }
+}
+
 // ------------------------------------------------------------------------------------- twiddle tables on device
 // The step before the path: the reference fills its root / precon buffers on the host (main.cpp:46-55) and the loader
 // broadcasts them (ntt.cpp:544-571).  Here one thread per (limb, direction, k) computes
