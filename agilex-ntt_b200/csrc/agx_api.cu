@@ -5,7 +5,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "agx_ntt_kernels.cuh"
@@ -279,6 +281,54 @@ bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Pageable callers: results are staged in pinned chunks and copied to the caller's buffer by a helper thread, so that
+// the copy-out of chunk i runs beside the staging-in of chunk i+1 on the calling thread (one thread doing both moves
+// ~4 GB/s in each direction; two move ~2x that).  Chunks are drained strictly in order.
+class OutDrainer {
+    struct Item { void *dst; const void *src; size_t bytes; cudaEvent_t ev; };
+    Item items_[kSlots] = {};
+    std::atomic<size_t> issued_{0}, drained_{0};
+    std::atomic<int> err_{0};
+    std::atomic<bool> stop_{false};
+    std::thread th_;
+    int device_;
+    void run() {
+        cudaSetDevice(device_);
+        for (size_t i = 0;; i++) {
+            while (issued_.load(std::memory_order_acquire) <= i) {
+                if (stop_.load(std::memory_order_acquire)) return;
+                std::this_thread::yield();
+            }
+            const Item it = items_[i % kSlots];
+            const cudaError_t e = cudaEventSynchronize(it.ev);
+            if (e != cudaSuccess) err_.store((int)e);
+            else memcpy(it.dst, it.src, it.bytes);
+            drained_.store(i + 1, std::memory_order_release);
+        }
+    }
+public:
+    explicit OutDrainer(int device) : device_(device) {}
+    ~OutDrainer() { finish(); }
+    // before chunk i reuses its slot's staging buffers: chunk i - kSlots must have been copied out
+    void wait_slot_free(size_t i) {
+        if (i < (size_t)kSlots) return;
+        while (drained_.load(std::memory_order_acquire) < i - kSlots + 1) std::this_thread::yield();
+    }
+    void submit(size_t i, void *dst, const void *src, size_t bytes, cudaEvent_t ev) {
+        if (!th_.joinable()) th_ = std::thread(&OutDrainer::run, this);
+        items_[i % kSlots] = Item{dst, src, bytes, ev};
+        issued_.store(i + 1, std::memory_order_release);
+    }
+    int finish() {
+        if (th_.joinable()) {
+            while (drained_.load(std::memory_order_acquire) < issued_.load(std::memory_order_acquire)) std::this_thread::yield();
+            stop_.store(true, std::memory_order_release);
+            th_.join();
+        }
+        return err_.load();
+    }
+};
+
 int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
     HostPipe &P = c->pipe;
     if (!P.stream[0]) {
@@ -326,16 +376,15 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
     HostPipe &P = c->pipe;
     const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
     const size_t chunk_polys = P.cap / poly_bytes;
-    struct Pending { uint32_t *dst; size_t bytes; };
-    Pending pend[kSlots] = {};
+    OutDrainer drain(c->device);
     size_t done = 0;
     for (size_t i = 0; done < B; i++) {
         const int sl = (int)(i % kSlots);
         const size_t cnt = B - done < chunk_polys ? B - done : chunk_polys, bytes = cnt * poly_bytes;
         const size_t off = done * poly_words;
         if (i >= (size_t)kSlots) {                       // slot reuse: its previous chunk must have drained
-            CK(cudaEventSynchronize(P.done[sl]));
-            if (pend[sl].dst) { memcpy(pend[sl].dst, P.p_out[sl], pend[sl].bytes); pend[sl].dst = nullptr; }
+            if (!pin_o) drain.wait_slot_free(i);
+            else if (!pin_a || !pin_b) CK(cudaEventSynchronize(P.done[sl]));
         }
         const uint32_t *src_a = h_a + off;
         if (!pin_a) { memcpy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
@@ -348,19 +397,18 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
         rc = launch(c, op, P.d_a[sl], P.d_a[sl], P.d_b[sl], cnt, P.stream[sl]);
         if (rc) {                                        // do not return with copies still touching caller memory
             for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(P.stream[k]);
+            drain.finish();
             return rc;
         }
         uint32_t *dst = h_out + off;
-        if (!pin_o) { pend[sl].dst = dst; pend[sl].bytes = bytes; dst = P.p_out[sl]; }
-        CK(cudaMemcpyAsync(dst, P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
+        CK(cudaMemcpyAsync(pin_o ? dst : P.p_out[sl], P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
         CK(cudaEventRecord(P.done[sl], P.stream[sl]));
+        if (!pin_o) drain.submit(i, dst, P.p_out[sl], bytes, P.done[sl]);
         done += cnt;
     }
-    for (int sl = 0; sl < kSlots; sl++) {
-        CK(cudaStreamSynchronize(P.stream[sl]));
-        if (pend[sl].dst) memcpy(pend[sl].dst, P.p_out[sl], pend[sl].bytes);
-    }
-    return AGX_OK;
+    rc = drain.finish();
+    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(P.stream[sl]));
+    return rc;
 }
 
 void pipe_destroy(HostPipe &P) {
@@ -439,17 +487,16 @@ int ref_flush(agx_ctx *c) {
     while ((1u << logn) < R.N) logn++;
     const int use_smem = frame_bytes <= (128u << 10);
     const unsigned threads = R.N / 2 < 1024 ? (R.N / 2 < 32 ? 32 : R.N / 2) : 1024;
-    struct Pending { uint64_t *dst; size_t bytes; };
-    Pending pend[kSlots] = {};
+    OutDrainer drain(c->device);
     size_t done = 0;
     for (size_t i = 0; done < R.frames; i++) {
         const int sl = (int)(i % kSlots);
         cudaStream_t st = R.stream[sl];
         const size_t cnt = R.frames - done < chunk_frames ? R.frames - done : chunk_frames, bytes = cnt * frame_bytes;
         const size_t off = done * N;
-        if (i >= (size_t)kSlots && (!pin_in || !pin_out)) {          // staging buffers of this slot are about to be reused
-            CK(cudaEventSynchronize(R.done[sl]));
-            if (pend[sl].dst) { memcpy(pend[sl].dst, R.p_out[sl], pend[sl].bytes); pend[sl].dst = nullptr; }
+        if (i >= (size_t)kSlots) {                                   // staging buffers of this slot are about to be reused
+            if (!pin_out) drain.wait_slot_free(i);
+            else if (!pin_in) CK(cudaEventSynchronize(R.done[sl]));
         }
         if (pin_in) {
             if (same) {
@@ -495,22 +542,18 @@ int ref_flush(agx_ctx *c) {
         rc = (int)cudaGetLastError();
         if (rc) {
             for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(R.stream[k]);
+            drain.finish();
             return rc;
         }
         uint64_t *dst = R.out + off;
-        if (!pin_out) { pend[sl].dst = dst; pend[sl].bytes = bytes; dst = R.p_out[sl]; }
-        CK(cudaMemcpyAsync(dst, R.d_out[sl], bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pin_out ? dst : R.p_out[sl], R.d_out[sl], bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(R.done[sl], st));
+        if (!pin_out) drain.submit(i, dst, R.p_out[sl], bytes, R.done[sl]);
         done += cnt;
     }
-    if (!pin_out) {                                                  // drain the staged results before returning
-        for (int sl = 0; sl < kSlots; sl++) {
-            CK(cudaStreamSynchronize(R.stream[sl]));
-            if (pend[sl].dst) memcpy(pend[sl].dst, R.p_out[sl], pend[sl].bytes);
-        }
-    }
+    rc = drain.finish();                                             // pageable results are complete on return
     R.busy = true;
-    return AGX_OK;
+    return rc;
 }
 
 }  // namespace
