@@ -12,6 +12,7 @@
 
 #include "agx_ntt_kernels.cuh"
 #include "agx_ntt_pers.cuh"
+#include "agx_ntt_tm.cuh"
 #include "agx_tables.h"
 
 using namespace agx;
@@ -68,6 +69,7 @@ struct agx_ctx {
     uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural, with n^-1 in inverse entry 0, when le == 0)
     uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
+    LimbConst lc0 = {};                                    // limb 0, passed by value in the kernel parameters
     unsigned long long *d_sum = nullptr;
     unsigned long long *d_trace = nullptr;                 // AGX_TRACE builds: phase timestamps of sampled CTAs
     uint64_t launches = 0;
@@ -110,6 +112,7 @@ int build_tables(agx_ctx *c) {
         x.bar_sh = (uint32_t)(k - 1);
         x.psi = psi; x.zero = 0;
     }
+    c->lc0 = lc[0];
     LimbGen *d_lg = nullptr;
     CK(cudaMalloc(&c->d_nat_fwd, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_nat_inv, entries * sizeof(uint2)));
@@ -141,13 +144,16 @@ int build_tables(agx_ctx *c) {
 }
 
 KParams kparams(const agx_ctx *c) {
-    return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->d_trace};
+    return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->d_trace, c->lc0};
 }
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
 // Persistent forward / inverse kernels (agx_ntt_pers.cuh) serve agx_ntt_fwd / agx_ntt_inv and the outer two launches
 // of the split polynomial product; AGX_PERSISTENT=0 builds the one-CTA-per-polynomial kernels instead (A/B runs).
+#ifndef AGX_TMEM
+#define AGX_TMEM 0
+#endif
 #ifndef AGX_PERSISTENT
 #define AGX_PERSISTENT 0
 #endif
@@ -179,7 +185,7 @@ int setup_persistent(agx_ctx *c) {
     return AGX_OK;
 }
 
-template <int LOGN, int LE>
+template <int LOGN, int LE, bool CL>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     using G = Geo<LOGN, LE>;
     const KParams p = kparams(c);
@@ -194,11 +200,12 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
 #define AGX_FWD(dst, src) ntt_fwd_pers_kernel<LOGN, LE><<<gridf, block, 0, s>>>(dst, src, p, Tu)
 #define AGX_INV(dst) ntt_inv_pers_kernel<LOGN, LE><<<gridi, block, 0, s>>>(dst, p, Tu)
 #else
-#define AGX_FWD(dst, src) ntt_fwd_loop_kernel<LOGN, LE, false><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu)
-#define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(dst, p, Tu)
+#define AGX_FWD(dst, src) ntt_fwd_loop_kernel<LOGN, LE, false, CL><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu)
+#define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(dst, p, Tu)
 #endif
     if (op == OP_FWD) {
-        AGX_FWD(out, out);
+        if constexpr (AGX_TMEM && LOGN == 12) ntt_fwd_tm_kernel<LOGN, LE, CL><<<(Tu + 1) / 2, 128, 0, s>>>(out, out, p, Tu);
+        else AGX_FWD(out, out);
         c->launches++;
     } else if (op == OP_INV) {
         AGX_INV(out);
@@ -206,7 +213,7 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     } else if (LOGN <= 10) {
         // n = 1024: forward(a), forward(b), pointwise, inverse fused in one launch (its 28 KB of code fits the
         // instruction cache; at n >= 2048 the fused kernel is 57-60 KB and runs 30 % slower than the split below)
-        polymul_loop_kernel<LOGN, LE><<<grid, block, 0, s>>>(out, a, b, p);
+        polymul_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(out, a, b, p);
         c->launches++;
     } else {
         // three launches, no scratch buffer: out = NTT(a); out = NTT(b) .* out; out = INTT(out)
@@ -216,7 +223,7 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
             const size_t total = T * G::N;
             pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, LOGN, total);
         } else {
-            ntt_fwd_loop_kernel<LOGN, LE, true><<<grid, block, 0, s>>>(out, b, out, p, Tu);
+            ntt_fwd_loop_kernel<LOGN, LE, true, CL><<<grid, block, 0, s>>>(out, b, out, p, Tu);
         }
         AGX_INV(out);
         c->launches += 3;
@@ -260,9 +267,10 @@ int launch(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *
     if (T == 0) return AGX_OK;
     if (T > 0x7fffffffull) return AGX_E_INVALID;
     switch (c->le ? c->logn : 0) {
-        case 12: return launch_fast<12, 6>(c, op, out, a, b, T, s);
-        case 11: return launch_fast<11, 6>(c, op, out, a, b, T, s);
-        case 10: return launch_fast<10, 5>(c, op, out, a, b, T, s);
+        // single-limb batches run the instantiation whose modulus constants are constant-bank operands
+        case 12: return c->L == 1 ? launch_fast<12, 6, true>(c, op, out, a, b, T, s) : launch_fast<12, 6, false>(c, op, out, a, b, T, s);
+        case 11: return c->L == 1 ? launch_fast<11, 6, true>(c, op, out, a, b, T, s) : launch_fast<11, 6, false>(c, op, out, a, b, T, s);
+        case 10: return c->L == 1 ? launch_fast<10, 5, true>(c, op, out, a, b, T, s) : launch_fast<10, 5, false>(c, op, out, a, b, T, s);
         default: return launch_generic(c, op, out, a, b, T, s);
     }
 }
@@ -588,6 +596,15 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
         c->q.assign(parms->q, parms->q + parms->nlimbs);
         c->psi.resize(c->L);
         int rc = build_tables(c);
+#if AGX_TMEM
+        // 8 CTAs x 10.8 KB of shared memory per SM must fit the carve-out
+        if (!rc && c->logn == 12) {
+            int pct = 64;
+            if (const char *e = getenv("AGX_TM_CARVEOUT")) pct = atoi(e);
+            rc = (int)cudaFuncSetAttribute(ntt_fwd_tm_kernel<12, 6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            if (!rc) rc = (int)cudaFuncSetAttribute(ntt_fwd_tm_kernel<12, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+#endif
 #if AGX_PERSISTENT
         if (!rc && c->le) rc = c->logn == 12 ? setup_persistent<12, 6>(c) : c->logn == 11 ? setup_persistent<11, 6>(c) : setup_persistent<10, 5>(c);
 #endif

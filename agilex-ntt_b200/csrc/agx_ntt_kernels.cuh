@@ -36,7 +36,16 @@ struct KParams {
     const LimbConst *lc;     // [L]
     uint32_t L;
     unsigned long long *trace;   // AGX_TRACE builds only: per-CTA phase timestamps (profiles/trace_phases.py)
+    LimbConst c0;                // limb 0's constants by value: kernel parameters live in the constant bank, so the
+                                 // butterfly's q / 2q / -q / -2q / 0 operands cost no register-file read when L == 1
 };
+
+// Per-limb constants of a polynomial: kernels instantiated with CL = true (single-limb batches) read them from the
+// parameter block, i.e. as constant-bank operands; CL = false loads the limb's entry of the table in global memory.
+#define AGX_LIMB_CONSTS(CL, p, limb)            \
+    LimbConst limb_consts_;                     \
+    if constexpr (!(CL)) limb_consts_ = (p).lc[limb]; \
+    const LimbConst &c = (CL) ? (p).c0 : limb_consts_
 
 // Timing-experiment switches (never set in the shipped library):
 //   AGX_TRACE=1   thread 0 of every 64th CTA stamps clock64() at phase boundaries of the forward kernel
@@ -318,7 +327,7 @@ __device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const
 // dst may equal src (in place: agx_ntt_fwd).  MUL: the three-launch polynomial product's middle step -- the spectrum
 // is multiplied pointwise by `mul` (the other operand's spectrum, same layout; may equal dst) before it is stored,
 // and left in [0,2q), which is what the inverse kernel accepts.
-template <int LOGN, int LE, bool MUL>
+template <int LOGN, int LE, bool MUL, bool CL>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
@@ -326,7 +335,7 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
+    AGX_LIMB_CONSTS(CL, p, limb);
     const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
     const uint2 *twc = p.twc_fwd + (size_t)limb * G::N;
     const uint32_t *gs = src + (size_t)poly * G::N;
@@ -412,7 +421,7 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
 #endif
 }
 
-template <int LOGN, int LE>
+template <int LOGN, int LE, bool CL>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
@@ -420,7 +429,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
+    AGX_LIMB_CONSTS(CL, p, limb);
     const uint2 *tw = p.tw_inv + (size_t)limb * G::N;
     const uint2 *twc = p.twc_inv + (size_t)limb * G::N;
     uint32_t *g = data + (size_t)poly * G::N;
@@ -459,7 +468,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 // (BASELINE.json config 4).  The forward stage code runs 4 times (2 operands x 2 passes) and the inverse stage code
 // twice, each from a single copy; NTT(a) waits in a second shared-memory buffer (own row per thread) while b is
 // transformed.  HBM traffic: 3 * n * 4 bytes per product.
-template <int LOGN, int LE>
+template <int LOGN, int LE, bool CL>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
 polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, KParams p) {
     using G = Geo<LOGN, LE>;
@@ -468,7 +477,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
-    const LimbConst c = p.lc[limb];
+    AGX_LIMB_CONSTS(CL, p, limb);
     const uint2 *twf = p.tw_fwd + (size_t)limb * G::N, *twfc = p.twc_fwd + (size_t)limb * G::N;
     const uint2 *twi = p.tw_inv + (size_t)limb * G::N, *twic = p.twc_inv + (size_t)limb * G::N;
     const size_t off = (size_t)poly * G::N;
