@@ -210,7 +210,7 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     } else if (op == OP_INV) {
         AGX_INV(out);
         c->launches++;
-    } else if (LOGN <= 10) {
+    } else if constexpr (LOGN <= 10) {
         // n = 1024: forward(a), forward(b), pointwise, inverse fused in one launch (its 28 KB of code fits the
         // instruction cache; at n >= 2048 the fused kernel is 57-60 KB and runs 30 % slower than the split below)
         polymul_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(out, a, b, p);
