@@ -59,6 +59,16 @@ __device__ __forceinline__ void gs_bfly_last(uint32_t &u, uint32_t &v, uint2 wn,
     v = csub(shoup_mul(d, w1n, c.negq), c.negq);
 }
 
+// Last inverse stage for a pair whose inputs already carry n^-1 (they are difference outputs of the stage before, whose
+// column-pass twiddles are stored pre-multiplied by n^-1): the plain butterfly with the unscaled twiddle w1; no multiply
+// on the sum.  u,v in [0,2q) -> outputs in [0,q).
+__device__ __forceinline__ void gs_bfly_last_prescaled(uint32_t &u, uint32_t &v, uint2 w1, const LimbConst &c) {
+    const uint32_t s = u + v + c.zero;
+    const uint32_t d = u + c.twoq - v;
+    u = csub(csub(s, c.neg2q), c.negq);
+    v = csub(shoup_mul(d, w1, c.negq), c.negq);
+}
+
 // [0,4q) -> [0,q)  (ntt.cpp:377-393)
 __device__ __forceinline__ uint32_t reduce4q(uint32_t v, const LimbConst &c) {
     return csub(csub(v, c.neg2q), c.negq);

@@ -324,6 +324,22 @@ __device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const
     if constexpr (J > 1) gs_stages_down_to1<LOGN, LE, J - 1>(x, a, c);
 }
 
+// Last inverse stage (global stage 0), with the n^-1 scaling spread over the last TWO stages: the column pass's
+// local stage 1 twiddles are stored pre-multiplied by n^-1, so its difference outputs -- x[E/4..E/2) and x[3E/4..E) --
+// arrive scaled and their last-stage pairs need the plain butterfly (one multiply); only the pairs fed by its sum
+// outputs take the two scaling multiplies (tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .); twc[TPP] = unscaled iroot1).
+// Saves E/4 Shoup multiplies per thread against scaling every last-stage pair.
+template <int LOGN, int LE>
+__device__ __forceinline__ void inv_last_stage(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw,
+                                               const uint2 *__restrict__ twc, const LimbConst &c) {
+    using G = Geo<LOGN, LE>;
+    const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1), w1 = __ldg(twc + G::TPP);
+#pragma unroll
+    for (int j = 0; j < G::E / 4; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
+#pragma unroll
+    for (int j = G::E / 4; j < G::E / 2; j++) gs_bfly_last_prescaled(x[j], x[j + G::E / 2], w1, c);
+}
+
 // dst may equal src (in place: agx_ntt_fwd).  MUL: the three-launch polynomial product's middle step -- the spectrum
 // is multiplied pointwise by `mul` (the other operand's spectrum, same layout; may equal dst) before it is stored,
 // and left in [0,2q), which is what the inverse kernel accepts.
@@ -455,11 +471,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
             poly_sync<G::TPP>();
         }
     }
-    {   // last stage (global stage 0) with n^-1 folded: tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .)
-        const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1);
-#pragma unroll
-        for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
-    }
+    inv_last_stage<LOGN, LE>(x, tw, twc, c);
 #pragma unroll
     for (int k = 0; k < G::E; k++) st_stream(g + tid + G::TPP * k, x[k]);
 }
@@ -533,11 +545,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
             poly_sync<G::TPP>();
         }
     }
-    {
-        const uint2 wn = __ldg(twi), w1n = __ldg(twi + 1);
-#pragma unroll
-        for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
-    }
+    inv_last_stage<LOGN, LE>(x, twi, twic, c);
 #pragma unroll
     for (int k = 0; k < G::E; k++) st_stream(out + off + tid + G::TPP * k, x[k]);
 }
@@ -826,7 +834,12 @@ __global__ void __launch_bounds__(256) gen_tables_kernel(uint2 *__restrict__ nat
         const int j = 31 - __clz(k), lt = (int)logn - le;
         const uint32_t gq = k - (1u << j), tpp = 1u << lt;
         const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
-        (inverse ? twc_inv : twc_fwd)[base + cpos] = natural;
+        uint2 cval = natural;
+        if (inverse && j == 1) {                                          // inv_last_stage: local stage 1 carries n^-1
+            const uint32_t ws = mulmod_dev(r, g.n_inv, g.q);
+            cval = make_uint2(ws, (uint32_t)(((uint64_t)ws << 32) / g.q));
+        }
+        (inverse ? twc_inv : twc_fwd)[base + cpos] = cval;
     }
 }
 

@@ -398,11 +398,7 @@ ntt_inv_pers_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
                 poly_sync<G::TPP>();
             }
         }
-        {   // last stage (global stage 0) with n^-1 folded: tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .)
-            const uint2 wn = __ldg(ls.tw), w1n = __ldg(ls.tw + 1);
-#pragma unroll
-            for (int j = 0; j < G::E / 2; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
-        }
+        inv_last_stage<LOGN, LE>(x, ls.tw, ls.twc, c);
         uint32_t *g = data + (size_t)poly * G::N;
 #pragma unroll
         for (int k = 0; k < G::E; k++) __stcs(g + tid + G::TPP * k, x[k]);
