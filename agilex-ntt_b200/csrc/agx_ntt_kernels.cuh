@@ -268,11 +268,29 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
 struct PassAddr {
     const uint4 *b4;
     const uint2 *b2;
+    const uint4 *b4b;    // inverse only: the "already scaled" twiddle variant (see kInvFold); == b4 in the row pass
 };
 
 template <int LOGN, int LE>
-__device__ __forceinline__ PassAddr pass_addr(const uint2 *__restrict__ table, uint32_t toff) {
-    return PassAddr{reinterpret_cast<const uint4 *>(table) + toff, table + (1u << (LOGN - LE)) + toff};
+__device__ __forceinline__ PassAddr pass_addr(const uint2 *__restrict__ table, uint32_t toff, uint32_t variant_b = 0u) {
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(table) + toff;
+    return PassAddr{b4, table + (1u << (LOGN - LE)) + toff, b4 + variant_b};
+}
+
+// Inverse transform, where n^-1 goes.  Every stage multiplies only its difference outputs, so n^-1 cannot ride on one
+// stage's twiddles alone.  It is folded into the column pass (the last LE stages) like this: local stage kInvFold
+// stores ALL its twiddles pre-multiplied by n^-1, which scales every coefficient whose register index has bit
+// half(kInvFold) set.  In the later stages J < kInvFold a pair whose index has any of the bits half(J+1..kInvFold) set
+// is already scaled and takes the unscaled twiddle (variant B, stored one 16-byte slot after variant A in the column
+// table); a pair with none of them set is still unscaled: its sum stays so, its difference takes the scaled twiddle
+// (variant A).  Only the E / 2^(kInvFold+1) last-stage pairs that were sums all the way need the two explicit scaling
+// multiplies.  The row pass runs the same stage code with b4b == b4 (both variants are the plain twiddle).
+constexpr int kInvFold = 3;
+template <int LE>
+__host__ __device__ constexpr int inv_fold_mask(int J) {   // index bits that mark a pair as already scaled at local stage J
+    int m = 0;
+    for (int jj = J + 1; jj <= kInvFold; jj++) m += (1 << LE) >> (jj + 1);
+    return J < kInvFold ? m : 0;
 }
 
 template <int LOGN, int LE, int J>
@@ -304,12 +322,25 @@ __device__ __forceinline__ void ct_stage(uint32_t (&x)[1 << LE], const PassAddr 
 template <int LOGN, int LE, int J>
 __device__ __forceinline__ void gs_stage(uint32_t (&x)[1 << LE], const PassAddr &a, const LimbConst &c) {
     constexpr int half = (1 << LE) >> (J + 1);
+    constexpr int mask = J >= 1 ? inv_fold_mask<LE>(J) : 0;
     uint2 w[1 << J];
     load_tw_generic<LOGN, LE, J>(w, a);
+    if constexpr (mask != 0) {
+        uint2 wb[1 << J];
+        PassAddr ab = a;
+        ab.b4 = a.b4b;
+        load_tw_generic<LOGN, LE, J>(wb, ab);
 #pragma unroll
-    for (int g = 0; g < (1 << J); g++)
+        for (int g = 0; g < (1 << J); g++)
 #pragma unroll
-        for (int i = 0; i < half; i++) gs_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], w[g], c);
+            for (int i = 0; i < half; i++)
+                gs_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], (i & mask) ? wb[g] : w[g], c);
+    } else {
+#pragma unroll
+        for (int g = 0; g < (1 << J); g++)
+#pragma unroll
+            for (int i = 0; i < half; i++) gs_bfly(x[g * 2 * half + i], x[g * 2 * half + i + half], w[g], c);
+    }
 }
 
 template <int LOGN, int LE, int J>
@@ -324,20 +355,21 @@ __device__ __forceinline__ void gs_stages_down_to1(uint32_t (&x)[1 << LE], const
     if constexpr (J > 1) gs_stages_down_to1<LOGN, LE, J - 1>(x, a, c);
 }
 
-// Last inverse stage (global stage 0), with the n^-1 scaling spread over the last TWO stages: the column pass's
-// local stage 1 twiddles are stored pre-multiplied by n^-1, so its difference outputs -- x[E/4..E/2) and x[3E/4..E) --
-// arrive scaled and their last-stage pairs need the plain butterfly (one multiply); only the pairs fed by its sum
-// outputs take the two scaling multiplies (tw[0] = (n^-1, .), tw[1] = (iroot1 * n^-1, .); twc[TPP] = unscaled iroot1).
-// Saves E/4 Shoup multiplies per thread against scaling every last-stage pair.
+// Last inverse stage (global stage 0).  With the n^-1 folding described at kInvFold only the pairs whose index has none
+// of the fold bits set are still unscaled and take the two scaling multiplies (tw[0] = (n^-1, .), tw[1] =
+// (iroot1 * n^-1, .)); all others arrive scaled and take the plain butterfly with the unscaled twiddle twc[TPP] = iroot1.
+// Saves (E/2)(1 - 2^-kInvFold) Shoup multiplies per thread against scaling every last-stage pair.
 template <int LOGN, int LE>
 __device__ __forceinline__ void inv_last_stage(uint32_t (&x)[1 << LE], const uint2 *__restrict__ tw,
                                                const uint2 *__restrict__ twc, const LimbConst &c) {
     using G = Geo<LOGN, LE>;
     const uint2 wn = __ldg(tw), w1n = __ldg(tw + 1), w1 = __ldg(twc + G::TPP);
+    constexpr int mask = inv_fold_mask<LE>(0);
 #pragma unroll
-    for (int j = 0; j < G::E / 4; j++) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
-#pragma unroll
-    for (int j = G::E / 4; j < G::E / 2; j++) gs_bfly_last_prescaled(x[j], x[j + G::E / 2], w1, c);
+    for (int j = 0; j < G::E / 2; j++) {
+        if ((j & mask) == 0) gs_bfly_last(x[j], x[j + G::E / 2], wn, w1n, c);
+        else gs_bfly_last_prescaled(x[j], x[j + G::E / 2], w1, c);
+    }
 }
 
 // dst may equal src (in place: agx_ntt_fwd).  MUL: the three-launch polynomial product's middle step -- the spectrum
@@ -461,7 +493,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
             a = pass_addr<LOGN, LE>(tw, tid);
             lds_row<LOGN, LE>(sm, x, tid);
         } else {                                     // column pass: stages LE-1 .. 1 (stage 0 below)
-            a = pass_addr<LOGN, LE>(twc, 0u);
+            a = pass_addr<LOGN, LE>(twc, 0u, 1u);
             lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
         }
         gs_stages_down_to1<LOGN, LE, LE - 1>(x, a, c);
@@ -535,7 +567,7 @@ polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, 
         if (pass == 0) {
             ad = pass_addr<LOGN, LE>(twi, tid);
         } else {
-            ad = pass_addr<LOGN, LE>(twic, 0u);
+            ad = pass_addr<LOGN, LE>(twic, 0u, 1u);
             lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
         }
         gs_stages_down_to1<LOGN, LE, LE - 1>(x, ad, c);
@@ -835,11 +867,12 @@ __global__ void __launch_bounds__(256) gen_tables_kernel(uint2 *__restrict__ nat
         const uint32_t gq = k - (1u << j), tpp = 1u << lt;
         const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
         uint2 cval = natural;
-        if (inverse && j == 1) {                                          // inv_last_stage: local stage 1 carries n^-1
+        if (inverse && j >= 1 && j <= kInvFold) {                         // variant A of the folded stages carries n^-1
             const uint32_t ws = mulmod_dev(r, g.n_inv, g.q);
             cval = make_uint2(ws, (uint32_t)(((uint64_t)ws << 32) / g.q));
         }
         (inverse ? twc_inv : twc_fwd)[base + cpos] = cval;
+        if (inverse && j >= 1) twc_inv[base + cpos + 2] = natural;        // variant B: one 16-byte slot further
     }
 }
 

@@ -385,7 +385,7 @@ ntt_inv_pers_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
                 a = pass_addr<LOGN, LE>(ls.tw, tid);
                 lds_row<LOGN, LE>(sm, x, tid);
             } else {                                     // column pass: stages LE-1 .. 1 (stage 0 below)
-                a = pass_addr<LOGN, LE>(ls.twc, 0u);
+                a = pass_addr<LOGN, LE>(ls.twc, 0u, 1u);
                 lds_columns<LOGN, LE>(reinterpret_cast<const uint32_t *>(sm), x, tid);
                 poly_sync<G::TPP>();                     // transpose read back: the buffer can receive the next polynomial
                 have_next = wc.answer(poly, T, next);
