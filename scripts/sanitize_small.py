@@ -26,15 +26,17 @@ for n in (4096, 2048, 1024, 256):
     assert (dc.cpu().numpy().view(np.uint32).reshape(a.shape) == P.polymul(a, b)).all()
     ctx.elementwise("mac", dc, da, db)
     ctx.close()
-p = A.RefPipeline()
-N, q = 1024, Q[0]
-tw, pre = O.tables_u64(N, q)
-xin = np.arange(2 * N, dtype=np.uint64)
-out = np.zeros(2 * N, dtype=np.uint64)
-p.ntt_input_kernel(xin, xin, np.array([q], dtype=np.uint64), tw, pre, 2)
-p.fwd_ntt_kernel(0)
-p.ntt_output_kernel(out, 2)
-p.wait()
-assert (out == O.ref_fwd_u64(xin, xin, q, tw, pre, 2)).all()
-p.close()
+for N in (256, 1024, 16384):          # one-CTA-per-frame kernel; strided<3> + last pass; strided<4>, <3>, <3> + last pass
+    p = A.RefPipeline()
+    q = Q[0]
+    tw, pre = O.tables_u64(N, q)
+    xin = np.arange(2 * N, dtype=np.uint64)
+    xin2 = xin + np.uint64(1)
+    out = np.zeros(2 * N, dtype=np.uint64)
+    p.ntt_input_kernel(xin, xin2, np.array([q], dtype=np.uint64), tw, pre, 2)
+    p.fwd_ntt_kernel(0)
+    p.ntt_output_kernel(out, 2)
+    p.wait()
+    assert (out == O.ref_fwd_u64(xin, xin2, q, tw, pre, 2)).all()
+    p.close()
 print("sanitize_small ok")
