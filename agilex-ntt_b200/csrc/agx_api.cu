@@ -203,8 +203,12 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
 #define AGX_FWD(dst, src) ntt_fwd_loop_kernel<LOGN, LE, false, CL><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu)
 #define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(dst, p, Tu)
 #endif
+#ifndef AGX_FWD_TMA
+#define AGX_FWD_TMA 0
+#endif
     if (op == OP_FWD) {
-        if constexpr (AGX_TMEM && LOGN == 12) ntt_fwd_tm_kernel<LOGN, LE, CL><<<(Tu + 1) / 2, 128, 0, s>>>(out, out, p, Tu);
+        if constexpr (AGX_FWD_TMA != 0) ntt_fwd_tma_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(out, out, p, Tu);
+        else if constexpr (AGX_TMEM && LOGN == 12) ntt_fwd_tm_kernel<LOGN, LE, CL><<<(Tu + 1) / 2, 128, 0, s>>>(out, out, p, Tu);
         else AGX_FWD(out, out);
         c->launches++;
     } else if (op == OP_INV) {

@@ -354,6 +354,58 @@ ntt_fwd_pers_kernel(uint32_t *dst, const uint32_t *src, KParams p, uint32_t T) {
     }
 }
 
+// One-shot forward kernel whose input arrives by ONE TMA bulk copy into the (still empty) transpose buffer instead of
+// 64 coalesced LDG.32 per thread: experiment AGX_FWD_TMA=1 (profiles/r01_experiments.md).
+template <int LOGN, int LE, bool CL>
+__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+ntt_fwd_tma_kernel(uint32_t *dst, const uint32_t *src, KParams p, uint32_t T) {
+    using G = Geo<LOGN, LE>;
+    __shared__ __align__(128) uint4 sm[G::SMEM_CHUNKS];
+    __shared__ __align__(8) uint64_t mbar;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t poly = blockIdx.x;
+    const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
+    AGX_LIMB_CONSTS(CL, p, limb);
+    const uint2 *tw = p.tw_fwd + (size_t)limb * G::N;
+    const uint2 *twc = p.twc_fwd + (size_t)limb * G::N;
+    const uint32_t *gs = src + (size_t)poly * G::N;
+    constexpr uint32_t BYTES = 4u << LOGN;
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        mbar_expect_tx(&mbar, BYTES);
+        bulk_g2s(sm, gs, BYTES, &mbar);
+    }
+    prefetch_ahead<LOGN, G::TPP>(gs, poly, T, tid);
+    poly_sync<G::TPP>();
+    mbar_wait(&mbar, 0);
+    uint32_t x[G::E];
+    const uint32_t *swl = reinterpret_cast<const uint32_t *>(sm);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        PassAddr a;
+        if (pass == 0) {
+            a = pass_addr<LOGN, LE>(twc, 0u);
+#pragma unroll
+            for (int k = 0; k < G::E; k++) x[k] = swl[tid + G::TPP * k];
+        } else {
+            a = pass_addr<LOGN, LE>(tw, tid);
+            lds_row<LOGN, LE>(sm, x, tid);
+        }
+        if (G::LT == LE || pass == 0) ct_stage<LOGN, LE, 0>(x, a, c);
+        ct_stages_from<LOGN, LE, 1>(x, a, c);
+        if (pass == 0) {
+            poly_sync<G::TPP>();                         // every thread has taken its columns out of the linear image
+            sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
+            poly_sync<G::TPP>();
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
+    sts_row<LOGN, LE>(sm, x, tid);
+    poly_sync<G::TPP>();
+    smem_to_global<LOGN, LE>(sm, dst + (size_t)poly * G::N, tid);
+}
+
 // ----------------------------------------------------------------------------------------------------- inverse
 template <int LOGN, int LE>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
