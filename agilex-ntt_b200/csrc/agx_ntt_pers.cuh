@@ -109,43 +109,6 @@ __device__ __forceinline__ void half_to_global(const uint4 *ob, uint32_t *g, uin
         __stcs(g4 + i * H::ROWS_PER_STEP * G::CPR, s[i * H::ROWS_PER_STEP * H::HP4]);
 }
 
-// Warp-local output staging in ROUNDS of E/R words per row: a warp's 32 rows are contiguous in the polynomial, so the
-// warp can stage and copy them out on its own (__syncwarp instead of CTA barriers) through a 32-row buffer whose rows
-// hold E/R words + 16 bytes of padding.  R = 4 at n = 4096 keeps the buffer at 2.5 KB per warp, which leaves the
-// unified L1/shared array enough L1 to keep the row pass's twiddle table resident.
-template <int LOGN, int LE, int R>
-struct WarpStage {
-    using G = Geo<LOGN, LE>;
-    static constexpr int QC = G::CPR / R;          // chunks per row per round
-    static constexpr int QP4 = QC + 1;             // pitch in chunks (odd)
-    static constexpr int WARP_CHUNKS = 32 * QP4;
-    static constexpr int RPI = 32 / QC;            // rows covered by one copy-out instruction of the warp
-    static_assert(QC >= 1 && (QC & (QC - 1)) == 0 && QC <= 8, "chunks per round");
-};
-
-template <int LOGN, int LE, int R>
-__device__ __forceinline__ void warp_stage_out(uint4 *wb, const uint32_t (&x)[1 << LE], uint32_t *g_warp, uint32_t lane) {
-    using G = Geo<LOGN, LE>;
-    using W = WarpStage<LOGN, LE, R>;
-    uint4 *mine = wb + lane * W::QP4;
-    const uint32_t row = lane % W::RPI, cc = lane / W::RPI;
-    const uint4 *s = wb + row * W::QP4 + cc;
-    uint4 *g4 = reinterpret_cast<uint4 *>(g_warp) + row * G::CPR + cc;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        if (r) __syncwarp();
-#pragma unroll
-        for (int c = 0; c < W::QC; c++) {
-            const int j = 4 * (r * W::QC + c);
-            mine[c] = make_uint4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 32 / W::RPI; i++)
-            __stcs(g4 + i * W::RPI * G::CPR + r * W::QC, s[i * W::RPI * W::QP4]);
-    }
-}
-
 // padded-image cp.async of one polynomial (the asynchronous twin of global_to_smem)
 template <int LOGN, int LE>
 __device__ __forceinline__ void global_to_smem_async(uint4 *sm, const uint32_t *g, uint32_t tid) {
@@ -246,15 +209,7 @@ ntt_fwd_pers_kernel(uint32_t *dst, const uint32_t *src, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
     using H = HalfGeo<LOGN, LE>;
     __shared__ __align__(128) uint4 sm[G::SMEM_CHUNKS];   // landing zone (linear image) / transpose buffer (padded image)
-#ifndef AGX_PERS_ROUNDS
-#define AGX_PERS_ROUNDS 4
-#endif
-#if AGX_PERS_ROUNDS
-    using W = WarpStage<LOGN, LE, (G::CPR >= 8 ? AGX_PERS_ROUNDS : 2)>;
-    __shared__ __align__(16) uint4 ob[(G::TPP / 32) * W::WARP_CHUNKS];   // per-warp output staging
-#else
     __shared__ __align__(16) uint4 ob[H::CHUNKS];         // output staging, half a row per thread
-#endif
     __shared__ __align__(16) uint4 clc_resp;
     __shared__ __align__(8) uint64_t mbar, clc_bar;
     const uint32_t tid = threadIdx.x;
@@ -323,10 +278,6 @@ ntt_fwd_pers_kernel(uint32_t *dst, const uint32_t *src, KParams p, uint32_t T) {
 #if AGX_TRACE
         tr_t = clock64();
 #endif
-#if AGX_PERS_ROUNDS
-        __syncwarp();                                    // previous polynomial's copy-out reads of this warp's buffer are done
-        warp_stage_out<LOGN, LE, (G::CPR >= 8 ? AGX_PERS_ROUNDS : 2)>(ob + (tid / 32) * W::WARP_CHUNKS, x, g + (tid / 32) * 32 * G::E, tid % 32);
-#else
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             if (h) poly_sync<G::TPP>();                  // first half has been copied out
@@ -334,7 +285,6 @@ ntt_fwd_pers_kernel(uint32_t *dst, const uint32_t *src, KParams p, uint32_t T) {
             poly_sync<G::TPP>();
             half_to_global<LOGN, LE>(ob, g, tid, h);
         }
-#endif
 #if AGX_TRACE
         tr_out += clock64() - tr_t;
         if (!have_next && tid == 0 && blockIdx.x < 8192) {
