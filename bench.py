@@ -367,7 +367,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--n", "--ntt-size", dest="n", type=int, default=N_DEFAULT,
+                    help="transform size (use --ntt-size under torchrun, whose own parser claims --n*)")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="polynomials per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=32768, help="polynomials in the bounded CPU sample")
