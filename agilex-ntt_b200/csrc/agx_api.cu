@@ -113,7 +113,6 @@ int build_tables(agx_ctx *c) {
         x.psi = psi; x.zero = 0;
     }
     c->lc0 = lc[0];
-    LimbGen *d_lg = nullptr;
     CK(cudaMalloc(&c->d_nat_fwd, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_nat_inv, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_lc, lc.size() * sizeof(LimbConst)));
@@ -130,15 +129,18 @@ int build_tables(agx_ctx *c) {
         CK(cudaMemset(c->d_twc_fwd, 0, entries * sizeof(uint2)));
         CK(cudaMemset(c->d_twc_inv, 0, entries * sizeof(uint2)));
     }
-    CK(cudaMalloc(&d_lg, lg.size() * sizeof(LimbGen)));
-    CK(cudaMemcpy(d_lg, lg.data(), lg.size() * sizeof(LimbGen), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_lc, lc.data(), lc.size() * sizeof(LimbConst), cudaMemcpyHostToDevice));
-    const unsigned total = 2u * L * n;
-    gen_tables_kernel<<<(total + 255) / 256, 256>>>(c->d_nat_fwd, c->d_nat_inv, c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd,
-                                                    c->d_twc_inv, d_lg, L, c->logn, c->le);
-    c->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    LimbGen *d_lg = nullptr;
+    CK(cudaMalloc(&d_lg, lg.size() * sizeof(LimbGen)));
+    cudaError_t e = cudaMemcpy(d_lg, lg.data(), lg.size() * sizeof(LimbGen), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const unsigned total = 2u * L * n;
+        gen_tables_kernel<<<(total + 255) / 256, 256>>>(c->d_nat_fwd, c->d_nat_inv, c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd,
+                                                        c->d_twc_inv, d_lg, L, c->logn, c->le);
+        c->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
     cudaFree(d_lg);
     return (int)e;
 }
@@ -149,8 +151,11 @@ KParams kparams(const agx_ctx *c) {
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
-// Persistent forward / inverse kernels (agx_ntt_pers.cuh) serve agx_ntt_fwd / agx_ntt_inv and the outer two launches
-// of the split polynomial product; AGX_PERSISTENT=0 builds the one-CTA-per-polynomial kernels instead (A/B runs).
+// Build-time switches for the experiment kernels (all 0 in the shipped library, which launches one CTA per polynomial;
+// results of the A/B runs: profiles/r01_experiments.md):
+//   AGX_PERSISTENT=1  agx_ntt_pers.cuh: resident CTAs, TMA / cp.async staging, cluster-launch-control work stealing
+//   AGX_TMEM=1        agx_ntt_tm.cuh:   n = 4096 forward kernel with the coefficients parked in tensor memory
+//   AGX_FWD_TMA=1     one-shot forward kernel whose input arrives by one TMA bulk copy
 #ifndef AGX_TMEM
 #define AGX_TMEM 0
 #endif
@@ -247,8 +252,8 @@ int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const ui
         ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
         c->launches++;
     } else {
-        // generic polymul: out <- a; fwd(out); fwd(tmp=b copy) needs scratch: use the pipe's device buffer? keep it
-        // simple and exact: three generic launches on caller buffers when out aliases neither input.
+        // generic sizes: out <- NTT(a), tmp <- NTT(b) in a stream-ordered scratch buffer, out <- INTT(out .* tmp);
+        // supported when out does not alias b and a != b
         if (out == b || a == b) return AGX_E_UNSUPPORTED;
         const size_t bytes = T * c->n * 4;
         uint32_t *tmp = nullptr;
