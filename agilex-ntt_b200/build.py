@@ -67,6 +67,12 @@ def build_tools(force: bool = False) -> dict[str, str]:
         _run([nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-o", mb, src])
     if os.path.exists(mb):
         out["microbench"] = mb
+    tmb = os.path.join(BINDIR, "agx_tmem_microbench")
+    tsrc = os.path.join(CSRC, "agx_tmem_microbench.cu")
+    if os.path.exists(tsrc) and (force or _stale(tmb, [tsrc] + _sources(CSRC, (".cuh",)))):
+        _run([nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-o", tmb, tsrc])
+    if os.path.exists(tmb):
+        out["tmem_microbench"] = tmb
     drv_src = os.path.join(HOST, "main_compat.cpp")
     drv = os.path.join(BINDIR, "agx_main_compat")
     if os.path.exists(drv_src):
