@@ -73,6 +73,12 @@ struct agx_ctx {
     unsigned long long *d_sum = nullptr;
     unsigned long long *d_trace = nullptr;                 // AGX_TRACE builds: phase timestamps of sampled CTAs
     uint64_t launches = 0;
+    // TMA tensor maps over result buffers (forward kernels store through cp.async.bulk.tensor): the encoder entry
+    // point of the driver, and the maps of the most recently used (pointer, polynomial count) pairs
+    void *encode_tiled = nullptr;
+    struct MapSlot { const void *ptr = nullptr; size_t T = 0; CUtensorMap map; };
+    MapSlot maps[8];
+    unsigned map_next = 0;
     HostPipe pipe;
     RefState ref;
 };
@@ -151,6 +157,32 @@ KParams kparams(const agx_ctx *c) {
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
 
+#ifndef AGX_TMA_STORE
+#define AGX_TMA_STORE 1
+#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map over `T` result rows-of-polynomials at `ptr`: {32 words, E/32 halves, T * TPP rows}, box {32, 1, TPP},
+// 128-byte swizzle (tma_store_rows).  nullptr when the driver offers no encoder or the shape is out of range: the
+// caller then uses the staging-image kernel.
+const CUtensorMap *result_map(agx_ctx *c, void *ptr, size_t T, uint32_t E, uint32_t TPP) {
+    if (!AGX_TMA_STORE || !c->encode_tiled || (reinterpret_cast<uintptr_t>(ptr) & 15) || T * TPP > 0x7fffffffull) return nullptr;   // box coordinates are signed 32-bit
+    for (auto &m : c->maps)
+        if (m.ptr == ptr && m.T == T) return &m.map;
+    agx_ctx::MapSlot &m = c->maps[c->map_next++ % 8];
+    const cuuint64_t gdim[3] = {32, E / 32, (cuuint64_t)T * TPP};
+    const cuuint64_t gstr[2] = {128, (cuuint64_t)E * 4};
+    const cuuint32_t box[3] = {32, 1, TPP}, estr[3] = {1, 1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+        &m.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { m.ptr = nullptr; return nullptr; }
+    m.ptr = ptr; m.T = T;
+    return &m.map;
+}
+
 // Build-time switches for the experiment kernels (all 0 in the shipped library, which launches one CTA per polynomial;
 // results of the A/B runs: profiles/r01_experiments.md):
 //   AGX_PERSISTENT=1  agx_ntt_pers.cuh: resident CTAs, TMA / cp.async staging, cluster-launch-control work stealing
@@ -196,6 +228,7 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     const KParams p = kparams(c);
     const dim3 grid((unsigned)T), block(G::TPP);
     const uint32_t Tu = (uint32_t)T;
+    static const CUtensorMap no_map = {};          // kernels instantiated without the TMA store ignore their map
 #if AGX_PERSISTENT
 #if AGX_PERS_SCHED
     const dim3 gridf = grid, gridi = grid;         // one CTA index per polynomial; resident CTAs steal the pending ones
@@ -205,7 +238,13 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
 #define AGX_FWD(dst, src) ntt_fwd_pers_kernel<LOGN, LE><<<gridf, block, 0, s>>>(dst, src, p, Tu)
 #define AGX_INV(dst) ntt_inv_pers_kernel<LOGN, LE><<<gridi, block, 0, s>>>(dst, p, Tu)
 #else
-#define AGX_FWD(dst, src) ntt_fwd_loop_kernel<LOGN, LE, false, CL><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu)
+#define AGX_FWD(dst, src)                                                                                              \
+    do {                                                                                                               \
+        if (const CUtensorMap *tm = result_map(c, dst, T, G::E, G::TPP))                                               \
+            ntt_fwd_loop_kernel<LOGN, LE, false, CL, true><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu, *tm);      \
+        else                                                                                                           \
+            ntt_fwd_loop_kernel<LOGN, LE, false, CL, false><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu, no_map);  \
+    } while (0)
 #define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(dst, p, Tu)
 #endif
 #ifndef AGX_FWD_TMA
@@ -232,7 +271,7 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
             const size_t total = T * G::N;
             pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, LOGN, total);
         } else {
-            ntt_fwd_loop_kernel<LOGN, LE, true, CL><<<grid, block, 0, s>>>(out, b, out, p, Tu);
+            ntt_fwd_loop_kernel<LOGN, LE, true, CL, false><<<grid, block, 0, s>>>(out, b, out, p, Tu, no_map);
         }
         AGX_INV(out);
         c->launches += 3;
@@ -287,6 +326,7 @@ int launch(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *
 int check_dev_call(agx_ctx *c, const void *p, size_t B) {
     if (!c || !c->has_parms) return AGX_E_INVALID;
     if (B && !p) return AGX_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(p) & 15) return AGX_E_INVALID;   // 16-byte vector accesses and tensor copies
     return set_device(c);
 }
 
@@ -588,6 +628,15 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
     if (!c) return AGX_E_NOMEM;
     c->device = device;
     cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            c->encode_tiled = fn;
+        else
+            cudaGetLastError();
+    }
     // kernels that take more than 48 KB of dynamic shared memory opt in per device (function attributes are
     // per-context state, so this is repeated for every context rather than cached in a process-wide flag)
     {
@@ -675,6 +724,7 @@ int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db
     int rc = check_dev_call(c, dc, B);
     if (rc) return rc;
     if (B && (!da || !db)) return AGX_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db)) & 15) return AGX_E_INVALID;
     return launch(c, OP_MUL, dc, da, db, B, (cudaStream_t)stream);
 }
 

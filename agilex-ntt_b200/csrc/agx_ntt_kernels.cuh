@@ -24,6 +24,8 @@
 //                         natural 2^s + T*c + kk  ->  2^s + ((kk>>1)*TPP + T)*2 + (kk&1)   (c >= 2)
 //   inverse table: entry 0 = (n^-1, .), entry 1 = (psi^-bitrev(1) * n^-1, .)
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "agx_arith.cuh"
 
 namespace agx {
@@ -238,6 +240,75 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
     for (int i = 0; i < G::N / 4 / G::TPP; i++) s[i * (G::TPP / G::CPR) * G::PITCH4] = v[i];
 }
 
+// ---------------------------------------------------------------------------------- results by TMA tensor store
+// Forward results leave the SM as E/32 asynchronous tensor stores issued by ONE thread instead of 16 x (LDS.128 +
+// STG.128) per thread.  Every thread writes its row into DENSE shared-memory tiles -- one per 32-word half of the rows,
+// TPP rows x 128 bytes each -- in the TMA engine's 128-byte swizzle (16-byte chunk index XOR (row & 7): conflict-free
+// STS.128 at a pitch of 128 bytes); after a proxy fence and a barrier one thread issues cp.async.bulk.tensor (3-D map
+// over the destination batch: {32 words, E/32 halves, T*TPP rows}, box {32, 1, TPP}) and waits only until the tiles have
+// been READ.  The tiles must start on a 1024-byte boundary (the swizzle is a function of address bits 7..9).
+// Measured and not kept (profiles/r01_experiments.md): the same tiles for the transpose as well, tensor LOADS for the
+// inverse kernel's input, tensor stores for its output.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "AGX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra AGX_DONE;\n"
+        "bra AGX_WAIT;\n"
+        "AGX_DONE:\n"
+        "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+template <int LOGN, int LE>
+struct Swz {
+    using G = Geo<LOGN, LE>;
+    static constexpr int HALVES = G::E / 32;
+    static constexpr int HALF_BYTES = G::TPP * 128;
+    static constexpr int HALF_WORDS = G::TPP * 32;
+    static constexpr int BYTES = HALVES * HALF_BYTES;    // = 4n
+};
+
+template <int LOGN, int LE>
+__device__ __forceinline__ void sts_row_swz(uint4 *sm, const uint32_t (&x)[1 << LE], uint32_t tid) {
+    using S = Swz<LOGN, LE>;
+    char *base = reinterpret_cast<char *>(sm) + tid * 128;
+    const uint32_t swz = (tid & 7) << 4;
+#pragma unroll
+    for (int cc = 0; cc < 8; cc++) {
+        char *at = base + ((cc << 4) ^ swz);
+#pragma unroll
+        for (int h = 0; h < S::HALVES; h++) {
+            const int j = 4 * (8 * h + cc);
+            *reinterpret_cast<uint4 *>(at + h * S::HALF_BYTES) = make_uint4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+    }
+}
+
+// one thread: the CTA's polynomial, shared-memory tiles -> global, asynchronously; returns when the tiles have been read
+template <int LOGN, int LE>
+__device__ __forceinline__ void tma_store_poly(const uint4 *sm, const CUtensorMap *map, uint32_t poly) {
+    using G = Geo<LOGN, LE>;
+    using S = Swz<LOGN, LE>;
+#pragma unroll
+    for (int h = 0; h < S::HALVES; h++)
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                     "r"(smem_u32(reinterpret_cast<const char *>(sm) + h * S::HALF_BYTES)), "r"(0), "r"(h), "r"(poly * G::TPP)
+                     : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the engine's reads
+}
+
 // minimum resident CTAs per SM requested from ptxas (sets the register cap): 64 coefficients/thread -> 512 threads
 // per SM (128 registers each), 32 coefficients/thread -> 768 threads (85 registers).
 #ifndef AGX_THREADS_E64
@@ -375,11 +446,14 @@ __device__ __forceinline__ void inv_last_stage(uint32_t (&x)[1 << LE], const uin
 // dst may equal src (in place: agx_ntt_fwd).  MUL: the three-launch polynomial product's middle step -- the spectrum
 // is multiplied pointwise by `mul` (the other operand's spectrum, same layout; may equal dst) before it is stored,
 // and left in [0,2q), which is what the inverse kernel accepts.
-template <int LOGN, int LE, bool MUL, bool CL>
+// TMA: results leave through tma_store_rows (dst is then described by `tmap`); otherwise through the padded staging
+// image and coalesced 16-byte stores.
+template <int LOGN, int LE, bool MUL, bool CL, bool TMA = false>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KParams p, uint32_t T) {
+ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KParams p, uint32_t T,
+                    const __grid_constant__ CUtensorMap tmap) {
     using G = Geo<LOGN, LE>;
-    __shared__ uint4 sm[G::SMEM_CHUNKS];
+    __shared__ __align__(1024) uint4 sm[G::SMEM_CHUNKS];
     const uint32_t tid = threadIdx.x;
     const uint32_t poly = blockIdx.x;
     const uint32_t limb = p.L == 1 ? 0 : poly % p.L;
@@ -460,11 +534,19 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
         for (int cc = 0; cc < G::CPR; cc++) __stcs(g4 + cc, make_uint4(x[4 * cc], x[4 * cc + 1], x[4 * cc + 2], x[4 * cc + 3]));
     }
 #else
-    sts_row<LOGN, LE>(sm, x, tid);                   // own row only: no barrier needed before
-    poly_sync<G::TPP>();
-    AGX_STAMP(14);
-    smem_to_global<LOGN, LE>(sm, g, tid);
-    AGX_STAMP(15);
+    if constexpr (TMA) {
+        poly_sync<G::TPP>();                         // the dense tiles overlap other threads' rows of the padded image
+        sts_row_swz<LOGN, LE>(sm, x, tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+        poly_sync<G::TPP>();
+        if (tid == 0) tma_store_poly<LOGN, LE>(sm, &tmap, poly);
+    } else {
+        sts_row<LOGN, LE>(sm, x, tid);               // own row only: no barrier needed before
+        poly_sync<G::TPP>();
+        AGX_STAMP(14);
+        smem_to_global<LOGN, LE>(sm, g, tid);
+        AGX_STAMP(15);
+    }
 #endif
 #endif
 }

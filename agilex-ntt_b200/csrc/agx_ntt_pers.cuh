@@ -33,26 +33,6 @@
 namespace agx {
 
 // ------------------------------------------------------------------------------------- async-copy primitives
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "AGX_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra AGX_DONE;\n"
-        "bra AGX_WAIT;\n"
-        "AGX_DONE:\n"
-        "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
 // global -> shared bulk copy by the TMA engine; bytes a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *b) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to dst are ordered first

@@ -26,7 +26,8 @@
  *     order in, BIT-REVERSED order out, outputs fully reduced to [0,q); inverse is Gentleman-Sande,
  *     bit-reversed in, natural out, n^-1 folded in.  psi = the minimal primitive 2n-th root of unity mod q.
  *   - Batched layout: uint32_t data[B][L][n] (B polynomials x L RNS limbs), row-major, in place.
- *     Inputs must be < 2q for the u32 entry points (uniform-mod-q data is < q).
+ *     Inputs must be < 2q for the u32 entry points (uniform-mod-q data is < q).  Device pointers must be 16-byte
+ *     aligned (anything from cudaMalloc is).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer calls only
  *     enqueue; completion follows normal stream semantics.  *_host calls return after the results are in
  *     host memory.

@@ -411,6 +411,9 @@ def test_argument_errors(A, torch):
     L = A.lib()
     assert L.agx_ntt_fwd(c._h, None, 4, None) == -1            # AGX_E_INVALID: null data with B > 0
     assert L.agx_ntt_fwd(c._h, None, 0, None) == 0             # empty batch is fine
+    buf = torch.zeros(4096 + 4, dtype=torch.int32, device="cuda")
+    assert L.agx_ntt_fwd(c._h, ctypes.c_void_p(buf.data_ptr() + 4), 1, None) == -1   # not 16-byte aligned
+    assert L.agx_ntt_inv(c._h, ctypes.c_void_p(buf.data_ptr() + 8), 1, None) == -1
     assert L.agx_polymul(c._h, ctypes.c_void_p(16), None, None, 1, None) == -1
     assert L.agx_ntt_fwd_host(c._h, None, None, 3) == -1
     assert L.agx_ntt_fwd_host(c._h, None, None, 0) == 0
