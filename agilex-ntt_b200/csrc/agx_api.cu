@@ -271,7 +271,10 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
             const size_t total = T * G::N;
             pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, LOGN, total);
         } else {
-            ntt_fwd_loop_kernel<LOGN, LE, true, CL, false><<<grid, block, 0, s>>>(out, b, out, p, Tu, no_map);
+            if (const CUtensorMap *tm = result_map(c, out, T, G::E, G::TPP))
+                ntt_fwd_loop_kernel<LOGN, LE, true, CL, true><<<grid, block, 0, s>>>(out, b, out, p, Tu, *tm);
+            else
+                ntt_fwd_loop_kernel<LOGN, LE, true, CL, false><<<grid, block, 0, s>>>(out, b, out, p, Tu, no_map);
         }
         AGX_INV(out);
         c->launches += 3;
