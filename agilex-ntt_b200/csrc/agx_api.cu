@@ -639,6 +639,7 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
             c->encode_tiled = fn;
         else
             cudaGetLastError();
+        if (getenv("AGX_NO_TMA")) c->encode_tiled = nullptr;   // force the staging-image kernels (tests cover both)
     }
     // kernels that take more than 48 KB of dynamic shared memory opt in per device (function attributes are
     // per-context state, so this is repeated for every context rather than cached in a process-wide flag)

@@ -499,3 +499,27 @@ def test_five_limbs_and_27bit_primes(A, torch):
         dz = torch.empty_like(dx)
         c.polymul(dz, dx, dy)
         assert (to_np(dz).reshape(x.shape) == P.polymul(x, y)).all()
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096])
+def test_forward_without_tensor_store(A, torch, monkeypatch, n):
+    """AGX_NO_TMA=1 at context creation selects the forward kernels that leave through the staging image and coalesced
+    16-byte stores (the path taken when the driver offers no tensor-map encoder): same bits as the TMA-store kernels."""
+    P = O.Plan(n, Q)
+    x = P.synthetic(5, seed=77)
+    want = P.fwd(x.copy())
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("AGX_NO_TMA", "1")
+        else:
+            monkeypatch.delenv("AGX_NO_TMA", raising=False)
+        c = A.Context(n, Q)
+        d = torch.from_numpy(x.view(np.int32)).cuda()
+        c.fwd(d)
+        assert (to_np(d).reshape(x.shape) == want).all(), ("no_tma" if no_tma else "tma")
+        a, b = P.synthetic(3, seed=5), P.synthetic(3, seed=6)
+        da, db = torch.from_numpy(a.view(np.int32)).cuda(), torch.from_numpy(b.view(np.int32)).cuda()
+        dc = torch.empty_like(da)
+        c.polymul(dc, da, db)
+        assert (to_np(dc).reshape(a.shape) == P.polymul(a, b)).all()
+        c.close()
