@@ -90,10 +90,10 @@ __host__ __device__ constexpr uint32_t tw_pos(int s, uint32_t T, uint32_t kk) {
     return c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * TPP + T) * 2 + (kk & 1);
 }
 
-// L2 prefetch of the polynomial a CTA slot will work on one wave later.  The CTA that owns it then finds its 16 KB in
+// L2 prefetch of the polynomial a CTA slot will work on about half a wave later.  The CTA that owns it then finds its 16 KB in
 // L2 (~250 clk) instead of paying a loaded-HBM round trip (~1.8 us measured as the load wait in the phase trace).
 #ifndef AGX_PREFETCH_DIST
-#define AGX_PREFETCH_DIST (8 * 148)
+#define AGX_PREFETCH_DIST (4 * 148)   // half a wave of n = 4096 CTAs ahead: 0.3-0.4 % better than a full wave in two A/B runs
 #endif
 template <int LOGN, int TPP>
 __device__ __forceinline__ void prefetch_ahead(const uint32_t *g_this, uint32_t poly, uint32_t T, uint32_t tid) {
@@ -356,7 +356,10 @@ __device__ __forceinline__ PassAddr pass_addr(const uint2 *__restrict__ table, u
 // table); a pair with none of them set is still unscaled: its sum stays so, its difference takes the scaled twiddle
 // (variant A).  Only the E / 2^(kInvFold+1) last-stage pairs that were sums all the way need the two explicit scaling
 // multiplies.  The row pass runs the same stage code with b4b == b4 (both variants are the plain twiddle).
-constexpr int kInvFold = 3;
+#ifndef AGX_INV_FOLD
+#define AGX_INV_FOLD 3
+#endif
+constexpr int kInvFold = AGX_INV_FOLD;
 template <int LE>
 __host__ __device__ constexpr int inv_fold_mask(int J) {   // index bits that mark a pair as already scaled at local stage J
     int m = 0;
