@@ -43,6 +43,7 @@ def _load() -> C.CDLL:
         "agx_ntt_inv": [vp, vp, C.c_size_t, vp],
         "agx_polymul": [vp, vp, vp, vp, C.c_size_t, vp],
         "agx_elementwise": [vp, C.c_int, vp, vp, vp, C.c_size_t, vp],
+        "agx_bitrev": [vp, vp, C.c_size_t, vp],
         "agx_ntt_fwd_host": [vp, vp, vp, C.c_size_t],
         "agx_ntt_inv_host": [vp, vp, vp, C.c_size_t],
         "agx_polymul_host": [vp, vp, vp, vp, C.c_size_t],
@@ -66,7 +67,7 @@ def _load() -> C.CDLL:
     return L
 
 
-EXPORTS = ("agx_create agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise "
+EXPORTS = ("agx_create agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise agx_bitrev "
            "agx_ntt_fwd_host agx_ntt_inv_host agx_polymul_host agx_host_alloc agx_host_free agx_fill_synthetic "
            "agx_checksum agx_ref_input agx_ref_fwd agx_ref_output agx_wait agx_error_string agx_launch_count "
            "agx_variant").split()
@@ -182,6 +183,11 @@ class Context:
         _ck(lib().agx_elementwise(self._h, self.EW[op], _dev_ptr(c), _dev_ptr(a), _dev_ptr(b), B, _stream_ptr(stream)),
             "agx_elementwise")
         return c
+
+    def bitrev(self, t, stream=None):
+        """Permute every polynomial of t by bit reversal, in place (natural <-> bit-reversed coefficient order)."""
+        _ck(lib().agx_bitrev(self._h, _dev_ptr(t), self._batch(t), _stream_ptr(stream)), "agx_bitrev")
+        return t
 
     def fill_synthetic(self, t, seed: int = 42, first_poly: int = 0, stream=None):
         _ck(lib().agx_fill_synthetic(self._h, _dev_ptr(t), self._batch(t), seed, first_poly, _stream_ptr(stream)),

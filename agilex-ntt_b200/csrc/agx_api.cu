@@ -647,6 +647,7 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
         cudaError_t e = cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bitrev_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e != cudaSuccess) { delete c; return (int)e; }
     }
     if (parms) {
@@ -750,6 +751,17 @@ int agx_elementwise(agx_ctx *c, int op, uint32_t *dc, const uint32_t *da, const 
         case EW_MUL: elementwise_kernel<EW_MUL><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
         default:     elementwise_kernel<EW_MAC><<<(unsigned)blocks, 256, 0, s>>>(c4, a4, b4, c->d_lc, c->L, c->logn, total4); break;
     }
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+int agx_bitrev(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
+    int rc = check_dev_call(c, d, B);
+    if (rc || B == 0) return rc;
+    const size_t T = B * c->L;
+    if (T > 0x7fffffffull) return AGX_E_INVALID;
+    const unsigned threads = c->n / 4 < 256 ? (c->n / 4 < 32 ? 32 : c->n / 4) : 256;
+    bitrev_rows_kernel<<<(unsigned)T, threads, (size_t)c->n * 4, (cudaStream_t)stream>>>(d, c->logn);
     c->launches++;
     return (int)cudaGetLastError();
 }

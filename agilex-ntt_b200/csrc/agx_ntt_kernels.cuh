@@ -796,6 +796,27 @@ __global__ void __launch_bounds__(1024) ref_fwd_u64_kernel(const uint64_t *__res
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) out[base + i] = X[i];
 }
 
+// ------------------------------------------------------------------------------------ coefficient-order adapter
+// The transforms keep the reference's orders (ntt.cpp: natural in, bit-reversed out; the inverse the other way round).
+// Callers that hold or want spectra in natural order (textbook / NTL-style code) permute with this kernel: row i of
+// each n-coefficient polynomial moves to bitrev(i).  An involution; in place; one CTA per polynomial, through shared
+// memory so that both the global reads and the global writes are coalesced 16-byte accesses.
+__global__ void __launch_bounds__(256) bitrev_rows_kernel(uint32_t *__restrict__ data, uint32_t logn) {
+    extern __shared__ uint32_t s[];
+    const uint32_t n = 1u << logn;
+    uint32_t *g = data + ((size_t)blockIdx.x << logn);
+    for (uint32_t i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(g + i);
+        s[__brev(i) >> (32 - logn)] = v.x;
+        s[__brev(i + 1) >> (32 - logn)] = v.y;
+        s[__brev(i + 2) >> (32 - logn)] = v.z;
+        s[__brev(i + 3) >> (32 - logn)] = v.w;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<uint4 *>(g + i) = make_uint4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+}
+
 // ------------------------------------------------------------- reference-shaped u64 forward: register-radix passes
 // The reference's native sizes (ntt.h:11-20: 1024, 8192, 16384, 32768) as a sequence of launches over a chunk of
 // frames that stays resident in L2: every pass keeps 2^LS coefficients of one butterfly network in registers and

@@ -86,6 +86,12 @@ int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t
 int agx_elementwise(agx_ctx *ctx, int op, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B,
                     void *stream);
 
+/* ---- coefficient-order adapter: permutes every n-coefficient row of [B][L][n] DEVICE data by bit reversal, in place
+ * (an involution).  The transforms keep the reference's orders (ntt.cpp:292-300: natural in, bit-reversed out; the
+ * inverse takes bit-reversed input); callers holding natural-order spectra convert with this call.  No reference
+ * counterpart. ---- */
+int agx_bitrev(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
+
 /* ---- the same on HOST pointers: chunked H2D / kernel / D2H pipeline over the context's own streams.
  * Pinned memory (agx_host_alloc, cudaHostAlloc, cudaHostRegister) is copied directly; pageable memory is staged
  * through internal pinned buffers.  h_out may equal h_in. ---- */

@@ -523,3 +523,30 @@ def test_forward_without_tensor_store(A, torch, monkeypatch, n):
         c.polymul(dc, da, db)
         assert (to_np(dc).reshape(a.shape) == P.polymul(a, b)).all()
         c.close()
+
+
+@pytest.mark.parametrize("n", [64, 1024, 4096, 32768])
+def test_bitrev_adapter_gives_the_textbook_order(A, torch, n):
+    """agx_bitrev permutes each polynomial by bit reversal in place: forward + bitrev is the natural-order spectrum
+    NTT(x)[k] = sum_j x[j] psi^((2k+1)j) (checked against the big-int definition at small n), and it is an involution."""
+    logn = n.bit_length() - 1
+    c = A.Context(n, Q[:2])
+    P = O.Plan(n, Q[:2])
+    x = P.synthetic(3, seed=9)
+    d = torch.from_numpy(x.view(np.int32)).cuda()
+    c.fwd(d)
+    y = to_np(d).reshape(x.shape).copy()
+    c.bitrev(d)
+    z = to_np(d).reshape(x.shape)
+    perm = np.array([O.bitrev(k, logn) for k in range(n)])
+    assert (z[..., perm] == y).all() and (z == y[..., perm]).all()
+    if n == 64:
+        for l, q in enumerate(Q[:2]):
+            psi = c.psi(l)
+            want = [sum(int(x[0, l, j]) * pow(psi, (2 * k + 1) * j, q) for j in range(n)) % q for k in range(n)]
+            assert z[0, l].tolist() == want
+    c.bitrev(d)
+    assert (to_np(d).reshape(x.shape) == y).all()
+    c.inv(d)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    c.close()
