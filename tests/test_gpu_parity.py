@@ -550,3 +550,56 @@ def test_bitrev_adapter_gives_the_textbook_order(A, torch, n):
     c.inv(d)
     assert (to_np(d).reshape(x.shape) == x).all()
     c.close()
+
+
+def _ntt_primes(count, n, below=1 << 30):
+    """The `count` largest primes q < below with q = 1 (mod 2n) (deterministic Miller-Rabin for 32-bit q)."""
+    def is_prime(q):
+        if q < 2:
+            return False
+        for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            if q % p == 0:
+                return q == p
+        d, s = q - 1, 0
+        while d % 2 == 0:
+            d, s = d // 2, s + 1
+        for a in (2, 3, 5, 7):
+            x = pow(a, d, q)
+            if x in (1, q - 1):
+                continue
+            for _ in range(s - 1):
+                x = x * x % q
+                if x == q - 1:
+                    break
+            else:
+                return False
+        return True
+    out, q = [], (below - 1) // (2 * n) * (2 * n) + 1
+    while len(out) < count:
+        if is_prime(q):
+            out.append(q)
+        q -= 2 * n
+    return tuple(out)
+
+
+@pytest.mark.parametrize("n,L,B", [(4096, 64, 1), (4096, 7, 3), (2048, 64, 2), (1024, 33, 5)])
+def test_many_limbs_odd_batches(A, torch, n, L, B):
+    """The maximum limb count (64), limb counts and batches that divide nothing, the largest primes below 2^30:
+    per-limb tables generated on the device, limb index = polynomial % L inside every kernel, odd transform counts."""
+    primes = _ntt_primes(L, n)
+    assert max(primes) < (1 << 30) and len(set(primes)) == L
+    c = ctx_for(A, n, primes)
+    P = O.Plan(n, primes)
+    x, y = P.synthetic(B, seed=31), P.synthetic(B, seed=32)
+    d = to_dev(torch, x)
+    c.fwd(d)
+    assert (to_np(d).reshape(x.shape) == P.fwd(x.copy())).all()
+    c.inv(d)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    dx, dy = to_dev(torch, x), to_dev(torch, y)
+    dz = torch.empty_like(dx)
+    c.polymul(dz, dx, dy)
+    assert (to_np(dz).reshape(x.shape) == P.polymul(x, y)).all()
+    out = np.empty_like(x)
+    c.fwd_host(x.copy(), out)
+    assert (out == P.fwd(x.copy())).all()
