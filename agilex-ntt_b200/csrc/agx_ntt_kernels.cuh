@@ -7,12 +7,16 @@
 // a single shared-memory transpose between them:
 //
 //   forward  pass A: thread t holds x[t + TPP*k]   -> stages 0..LE-1     (twiddles identical for all threads)
-//            transpose through XOR-swizzled smem (STS.32 columns -> LDS.128 rows, both conflict-free)
+//            transpose through a padded smem image (STS.32 columns -> LDS.128 rows, both conflict-free)
 //            pass B: thread T holds x[E*T .. E*T+E) -> stages LE..logn-1 (per-thread twiddles, coalesced 16-B loads
 //                                                      from a table stored in kernel order)
-//            final reduction to [0,q), staged through smem, written back with coalesced 16-B stores.
-//   inverse  is the mirror image (Gentleman-Sande), n^-1 folded into the last stage's twiddles.
-//   polymul  runs forward(a), parks it in smem, forward(b), pointwise Barrett, inverse -- one launch.
+//            final reduction to [0,q); rows into hardware-swizzled smem tiles, written back by TMA tensor stores
+//            (or, without a tensor-map encoder, staged through the padded image and coalesced 16-B stores).
+//   inverse  is the mirror image (Gentleman-Sande), n^-1 folded into the twiddles of the last four stages (kInvFold).
+//   polymul  n = 1024: forward(a), parked in smem, forward(b), pointwise Barrett, inverse -- one launch;
+//            n >= 2048: three launches (NTT(a); NTT(b) .* it; INTT), see agx_api.cu.
+// Also here: the generic any-n kernel, the limb-wise element-wise ops, the bit-reversal adapter, the reference-shaped
+// u64 pass kernels, the device-side table generator, synthetic data and checksum.
 //
 // The FPGA's X/X2/Xm double-buffer and reorder muxes (ntt.cpp:90-98, 160-289, 397-496) exist to dodge BRAM port
 // conflicts and have no arithmetic effect; they have no counterpart here.
