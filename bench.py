@@ -245,6 +245,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
 
     n, L, B = args.n, 1, args.batch
+    if args.total_batch:                        # strong scaling (SURVEY.md s.8(d) cfg 5): a fixed global batch split over the ranks
+        if args.total_batch % world:
+            raise SystemExit("bench.py: --total-batch must be a multiple of the number of GPUs")
+        B = args.total_batch // world
     ctx = A.Context(n, [PRIME], device=local_rank)
     data = torch.empty(B * L * n, dtype=torch.int32, device=dev)
     ctx.fill_synthetic(data, seed=SEED, first_poly=rank * B)      # shard = slice of the global synthetic batch
@@ -313,7 +317,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         line = {
             "metric": METRIC, "value": world * B * L * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "scaling": "strong" if args.total_batch else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"configs[1]: n={n} single 30-bit prime q={PRIME}, batch of {B} polynomials per GPU, "
                                    "forward launch + inverse launch in place",
                        "n": n, "nlimbs": L, "batch_per_gpu": B, "global_batch": world * B,
@@ -370,6 +374,8 @@ def main():
     ap.add_argument("--n", "--ntt-size", dest="n", type=int, default=N_DEFAULT,
                     help="transform size (use --ntt-size under torchrun, whose own parser claims --n*)")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="polynomials per GPU")
+    ap.add_argument("--total-batch", type=int, default=0,
+                    help="strong scaling: fixed global batch split contiguously over the GPUs (cfg 5 uses 2^31/n)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=32768, help="polynomials in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
