@@ -1,12 +1,14 @@
 // agx_ntt_tm.cuh -- n = 4096 forward / inverse kernels that keep the coefficients in TENSOR MEMORY.
 //
-// Why: the register-resident kernels (agx_ntt_kernels.cuh) need 64 coefficients + twiddles = 128 registers per thread,
-// which caps an SM at 512 threads = 4 warps per scheduler, and at 4 warps per scheduler the dependent
-// IMAD / IMAD.HI chains of the butterfly leave the multiply pipes idle a third of the time (the same butterfly stream
-// runs 15.6 butterflies/clk/SM at 4 warps per scheduler and 19.0 at 8: profiles/r01_tmem_microbench.jsonl).  Blackwell's
-// tensor memory is as large as the register file (512 columns x 128 lanes x 32 bit per SM), unused by this workload,
-// and tcgen05.ld/st.32x32b give every thread of a warp private columns of "its" lane -- a second register file with
-// a ~12-cycle access.  So a thread parks its 64 coefficients in 64 TMEM columns and works on 16 at a time:
+// EXPERIMENT (-DAGX_TMEM=1), bit-exact but slower than the shipped kernel (0.53 vs 0.49 ms; profiles/r01_experiments.md).
+//
+// Idea: the register-resident kernels (agx_ntt_kernels.cuh) need 64 coefficients + twiddles = 128 registers per thread,
+// which caps an SM at 512 threads = 4 warps per scheduler.  Blackwell's tensor memory is as large as the register file
+// (512 columns x 128 lanes x 32 bit per SM), unused by this workload, and tcgen05.ld/st.32x32b give every thread of a
+// warp private columns of "its" lane -- a second register file with a ~12-cycle access.  So a thread parks its 64
+// coefficients in 64 TMEM columns and works on 16 at a time.  What the measurement said: event-timed, the butterfly
+// stream runs 13.2 butterflies/clk/SM at 4 warps per scheduler and 14.1 at 8 (the multiply pipe is 90 % busy), so
+// doubling the resident warps is worth 7 %, less than the TMEM round trips (6 %) and the 15 % extra instructions cost.
 //
 //   pass over 64 coefficients x[0..64) (6 stages, stage j pairs x[k] with x[k + (32 >> j)]) =
 //     part 1: stages 0,1 on the 16 radix-4 groups {kl + 16*kh, kh < 4}, four groups (16 registers) per batch;
