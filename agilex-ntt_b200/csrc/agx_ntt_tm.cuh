@@ -1,4 +1,4 @@
-// agx_ntt_tm.cuh -- n = 4096 forward / inverse kernels that keep the coefficients in TENSOR MEMORY.
+// agx_ntt_tm.cuh -- n = 4096 forward kernel that keeps the coefficients in TENSOR MEMORY.
 //
 // EXPERIMENT (-DAGX_TMEM=1), bit-exact but slower than the shipped kernel (0.53 vs 0.49 ms; profiles/r01_experiments.md).
 //
@@ -18,7 +18,7 @@
 // With ~60 registers per thread 1024 threads (8 warps per scheduler) fit an SM.  A CTA is 128 threads = two
 // polynomials (warps 0-1 and 2-3: a warp reaches only the TMEM lanes 32*(warp%4).., so four warps use all 128 lanes
 // of the CTA's 64-column allocation; 8 CTAs x 64 columns = the whole TMEM).  Shared memory would not hold 16 full
-// transpose images per SM, and it does not have to: with the data parked in TMEM the transpose runs in four rounds
+// transpose images per SM, and it does not have to: with the data parked in TMEM the transpose runs in two rounds
 // through a 9 KB buffer per polynomial.  In round r warp w writes its coefficient chunk w^r (32 image rows, its own 32
 // columns) and reads back, from its own rows, the 32 words that warp w^r wrote -- the XOR makes the chunk a thread
 // receives land exactly in the TMEM columns it has just freed (TMEM addresses are warp-uniform, hence whole warps).
