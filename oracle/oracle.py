@@ -26,6 +26,10 @@ _LIB = None
 
 SEAL_PRIMES_30 = (1053818881, 1054015489, 1054212097)
 REF_SIZES = (32, 1024, 8192, 16384, 32768)              # include/kernel/ntt.h:11-20
+# NTT primes for the u64 datapath the reference kernel is written for (ntt.cpp:147-148, 344-363: 64-bit modulus, 64x64
+# -> high-64 Shoup product): the largest primes = 1 (mod 2^16) below 2^50, 2^60, 2^62 and 2^63.  The first three keep the
+# lazy range [0,4q) inside 64 bits; with the last one the arithmetic wraps mod 2^64 (the reference wraps identically).
+U64_PRIMES = {50: 1125899904679937, 60: 1152921504606584833, 62: 4611686018427322369, 63: 9223372036853661697}
 
 
 def build(force: bool = False) -> str:
@@ -192,6 +196,26 @@ def min_psi(n: int, q: int) -> int:
 
 def splitmix64(x: int) -> int:
     return int(lib().orc_splitmix64(x & 0xFFFFFFFFFFFFFFFF))
+
+
+def splitmix64_np(x: np.ndarray) -> np.ndarray:
+    """Vectorised splitmix64 over a uint64 array; equals orc_splitmix64 element-wise."""
+    with np.errstate(over="ignore"):
+        x = x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synthetic_u64(count: int, seed: int, mod: int) -> np.ndarray:
+    """count words: splitmix64(seed + i) mod `mod` (mod = q for reduced data, 4q for lazy inputs; mod < 2^64)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(count, dtype=np.uint64) + np.uint64(seed)
+    return splitmix64_np(idx) % np.uint64(mod)
+
+
+def is_prime(q: int) -> bool:
+    return bool(lib().orc_is_prime(q))
 
 
 def tables_u32(n: int, q: int, psi: int | None = None, inverse: bool = False):

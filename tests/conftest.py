@@ -42,3 +42,17 @@ def golden():
         parts = str(line).split(",")
         meta[parts[0]] = parts[1:]
     return g, meta
+
+
+@pytest.fixture(scope="session")
+def golden_u64():
+    """Outputs of the reference's own code on 50-/60-/62-/63-bit primes (tests/golden/make_golden.py: make_u64).
+    Returns (npz, cases): cases[name] = dict(N, q, psi, frames, seed_in, seed_in2, lazy, sha256)."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_fwd_golden_u64.npz"))
+    cases = {}
+    for line in g["meta"]:
+        name, N, q, psi, frames, s1, s2, lazy, sha = str(line).split(",")
+        cases[name] = dict(N=int(N), q=int(q), psi=int(psi), frames=int(frames), seed_in=int(s1), seed_in2=int(s2),
+                           lazy=bool(int(lazy)), sha256=sha)
+    return g, cases

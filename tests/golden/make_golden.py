@@ -1,4 +1,4 @@
-"""Generate tests/golden/ref_fwd_golden.npz by RUNNING THE REFERENCE'S OWN CODE.
+"""Generate tests/golden/ref_fwd_golden.npz and ref_fwd_golden_u64.npz by RUNNING THE REFERENCE'S OWN CODE.
 
 Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
 It builds oracle/_ref (the reference's src/kernel/ntt.cpp compiled against the host SYCL stand-in, see
@@ -48,9 +48,55 @@ CASES = [  # (name, N, q, kind, frames, seed)
 ]
 
 
+# u64 cases on the moduli the reference datapath is built for (ntt.cpp:147-148, 344-363): 50-, 60-, 62- and 63-bit NTT
+# primes q = 1 (mod 2^16).  Inputs lazy in [0,4q) (splitmix(seed+i) mod 4q), several frames, in2 != in (high halves come
+# from in2: ntt.cpp:587-589).  N <= 8192 stores the reference's outputs, N >= 16384 their SHA-256.
+# (name, N, bits, frames, seed_in, seed_in2, lazy)
+U64_CASES = [
+    ("u64_n1024_q50", 1024, 50, 3, 11, 12, True),
+    ("u64_n1024_q60", 1024, 60, 3, 13, 14, True),
+    ("u64_n1024_q62", 1024, 62, 2, 15, 16, False),   # 4q would reach 2^64: reduced inputs, lazy values inside still < 4q
+    ("u64_n1024_q63_wraps", 1024, 63, 2, 17, 18, False),   # 2q < 2^64 but 4q is not: arithmetic wraps mod 2^64
+    ("u64_n8192_q50", 8192, 50, 2, 21, 22, True),
+    ("u64_n8192_q60", 8192, 60, 2, 23, 24, True),
+    ("u64_n16384_q50", 16384, 50, 2, 31, 32, True),
+    ("u64_n16384_q60", 16384, 60, 2, 33, 34, True),
+    ("u64_n32768_q50", 32768, 50, 2, 41, 42, True),
+    ("u64_n32768_q60", 32768, 60, 2, 43, 44, True),
+]
+
+
+def u64_inputs(N, q, frames, seed_in, seed_in2, lazy):
+    mod = 4 * q if lazy else q
+    return O.synthetic_u64(N * frames, seed_in, mod), O.synthetic_u64(N * frames, seed_in2, mod)
+
+
+def make_u64():
+    out, meta = {}, []
+    for name, N, bits, frames, s1, s2, lazy in U64_CASES:
+        q = O.U64_PRIMES[bits]
+        assert O.is_prime(q) and q.bit_length() == bits and (q - 1) % (1 << 16) == 0 and q < 2**64
+        psi = O.min_psi(N, q)
+        assert pow(psi, N, q) == q - 1
+        roots, precons = O.tables_u64(N, q, psi)
+        x, x2 = u64_inputs(N, q, frames, s1, s2, lazy)
+        y = O.reference_fwd_u64(N, x, x2, q, roots, precons, frames)       # the reference's own code
+        if bits <= 62:
+            assert (y < q).all()
+        sha = hashlib.sha256(y.tobytes()).hexdigest()
+        if N <= 8192:
+            out[name] = y
+        meta.append(f"{name},{N},{q},{psi},{frames},{s1},{s2},{int(lazy)},{sha}")
+    out["meta"] = np.array(meta)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_fwd_golden_u64.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     assert os.path.isfile("/root/reference/src/kernel/ntt.cpp"), "needs the reference tree"
     O.build(force=True)
+    make_u64()
     out = {}
     meta = []
     for name, N, q, kind, frames, seed in CASES:

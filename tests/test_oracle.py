@@ -150,6 +150,40 @@ def test_golden_from_reference_code(golden):
     assert n_cases >= 10
 
 
+def u64_case_io(c):
+    mod = 4 * c["q"] if c["lazy"] else c["q"]
+    n = c["N"] * c["frames"]
+    return O.synthetic_u64(n, c["seed_in"], mod), O.synthetic_u64(n, c["seed_in2"], mod)
+
+
+def test_golden_u64_large_primes(golden_u64):
+    """The moduli the reference datapath is written for (64-bit, ntt.cpp:147-148, 344-363): 50-, 60- and 62-bit NTT
+    primes, lazy inputs, several frames, in2 != in -- restatement == outputs recorded from the reference's own code;
+    and a 63-bit prime, where [0,4q) no longer fits and the arithmetic wraps mod 2^64 exactly like the reference's."""
+    g, cases = golden_u64
+    assert len(cases) >= 10
+    for name, c in cases.items():
+        assert O.is_prime(c["q"]) and O.min_psi(c["N"], c["q"]) == c["psi"]
+        r, p = O.tables_u64(c["N"], c["q"], c["psi"])
+        x, x2 = u64_case_io(c)
+        y = O.ref_fwd_u64(x, x2, c["q"], r, p, c["frames"])
+        assert hashlib.sha256(y.tobytes()).hexdigest() == c["sha256"], name
+        if name in g.files:
+            assert (y == g[name]).all(), name
+        if c["q"] < 2**62:
+            assert (y < c["q"]).all()
+            # and it IS the transform: frame 0 against an independent big-int evaluation at a few output points
+            logn = c["N"].bit_length() - 1
+            f0 = [int(v) for v in x[:c["N"] // 2]] + [int(v) for v in x2[c["N"] // 2:c["N"]]]
+            for k in (0, 1, c["N"] - 1):
+                w = pow(c["psi"], 2 * O.bitrev(k, logn) + 1, c["q"])
+                acc, pw = 0, 1
+                for v in f0:
+                    acc += v * pw
+                    pw = pw * w % c["q"]
+                assert acc % c["q"] == int(y[k]), (name, k)
+
+
 def test_main_dummy_data_kat(golden):
     """main.cpp:49-55 dummy data through the u64 path; hashes from SURVEY.md App. A and from the reference run."""
     g, meta = golden
@@ -179,3 +213,9 @@ def test_live_reference_code(N):
     a = O.reference_fwd_u64(N, x, x2, q, r, p, frames)
     b = O.ref_fwd_u64(x, x2, q, r, p, frames)
     assert (a == b).all() and (a < q).all()
+    for bits in (50, 60, 63):          # the 64-bit moduli the kernel is written for; 63 bits wraps mod 2^64
+        q = O.U64_PRIMES[bits]
+        r, p = O.tables_u64(N, q)
+        mod = 4 * q if bits < 62 else q
+        x, x2 = O.synthetic_u64(N, 77 + bits, mod), O.synthetic_u64(N, 78 + bits, mod)
+        assert (O.reference_fwd_u64(N, x, x2, q, r, p, 1) == O.ref_fwd_u64(x, x2, q, r, p, 1)).all(), bits

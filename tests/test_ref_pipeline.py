@@ -71,6 +71,35 @@ def test_golden_lazy_and_multiframe(A, golden):
         assert (out == g[name]).all(), name
 
 
+def test_golden_u64_large_primes(A, golden_u64):
+    """50-, 60-, 62-bit NTT primes (the moduli the reference's 64-bit datapath exists for) and a 63-bit one whose lazy
+    range wraps mod 2^64: lazy inputs, several frames, in2 != in, N = 1024 ... 32768, against the outputs of the
+    reference's own code (stored for N <= 8192, SHA-256 for N >= 16384)."""
+    g, cases = golden_u64
+    for name, c in cases.items():
+        mod = 4 * c["q"] if c["lazy"] else c["q"]
+        n = c["N"] * c["frames"]
+        x, x2 = O.synthetic_u64(n, c["seed_in"], mod), O.synthetic_u64(n, c["seed_in2"], mod)
+        tw, pre = O.tables_u64(c["N"], c["q"], c["psi"])
+        out, _ = run_pipeline(A, x, x2, c["q"], tw, pre, c["frames"])
+        assert hashlib.sha256(out.tobytes()).hexdigest() == c["sha256"], name
+        if name in g.files:
+            assert (out == g[name]).all(), name
+
+
+@pytest.mark.parametrize("bits", [50, 60, 63])
+@pytest.mark.parametrize("N", [512, 2048, 16384, 32768])
+def test_large_primes_vs_restatement(A, N, bits):
+    """Sizes between the golden ones, against the C restatement (itself pinned on the same primes by the golden file)."""
+    q = O.U64_PRIMES[bits]
+    tw, pre = O.tables_u64(N, q)
+    frames = 3
+    mod = 4 * q if bits < 62 else q
+    x, x2 = O.synthetic_u64(N * frames, 5 + bits, mod), O.synthetic_u64(N * frames, 6 + bits, mod)
+    out, _ = run_pipeline(A, x, x2, q, tw, pre, frames)
+    assert (out == O.ref_fwd_u64(x, x2, q, tw, pre, frames)).all()
+
+
 def test_call_order_is_free_like_the_reference(A):
     """The reference's three kernels run concurrently and meet through pipes; submission order does not matter."""
     N, q = 1024, O.SEAL_PRIMES_30[0]
