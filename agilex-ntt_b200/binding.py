@@ -36,6 +36,8 @@ def _load() -> C.CDLL:
     vp = C.c_void_p
     sigs = {
         "agx_create": [C.POINTER(vp), C.POINTER(_Parms), C.c_int],
+        "agx_create_tables": [C.POINTER(vp), C.POINTER(_Parms), _u32p, C.c_int],
+        "agx_set_tables": [vp, C.c_uint32, C.c_int, _u32p, _u32p],
         "agx_destroy": [vp],
         "agx_get_psi": [vp, C.c_uint32, _u32p],
         "agx_get_tables": [vp, C.c_uint32, C.c_int, _u32p, _u32p],
@@ -55,6 +57,8 @@ def _load() -> C.CDLL:
         "agx_ref_fwd": [vp, C.c_uint32],
         "agx_ref_output": [vp, _u64p, C.c_int32],
         "agx_wait": [vp],
+        "agx_ref_fwd_dev": [vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, vp],
+        "agx_measure_butterfly_peak": [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "agx_launch_count": [vp, _u64p],
         "agx_variant": [vp, C.c_char_p, C.c_size_t],
     }
@@ -67,7 +71,7 @@ def _load() -> C.CDLL:
     return L
 
 
-EXPORTS = ("agx_create agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise agx_bitrev "
+EXPORTS = ("agx_create agx_create_tables agx_set_tables agx_ref_fwd_dev agx_measure_butterfly_peak agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise agx_bitrev "
            "agx_ntt_fwd_host agx_ntt_inv_host agx_polymul_host agx_host_alloc agx_host_free agx_fill_synthetic "
            "agx_checksum agx_ref_input agx_ref_fwd agx_ref_output agx_wait agx_error_string agx_launch_count "
            "agx_variant").split()
@@ -110,7 +114,8 @@ def _stream_ptr(stream) -> int:
 class Context:
     """One (n, primes) parameter set bound to one GPU: owns the device twiddle tables and the host pipeline."""
 
-    def __init__(self, n: int, primes, device: int = 0):
+    def __init__(self, n: int, primes, device: int = 0, psi=None):
+        """psi: the caller's primitive 2n-th root per limb (agx_create_tables); None = the minimal root (agx_create)."""
         self._h = C.c_void_p()
         self.n = int(n)
         self.logn = self.n.bit_length() - 1
@@ -119,7 +124,34 @@ class Context:
         self.device = device
         self._q = (C.c_uint32 * self.L)(*self.primes)
         p = _Parms(self.n, self.logn, self.L, C.cast(self._q, _u32p))
-        _ck(lib().agx_create(C.byref(self._h), C.byref(p), device), "agx_create")
+        if psi is None:
+            _ck(lib().agx_create(C.byref(self._h), C.byref(p), device), "agx_create")
+        else:
+            psi = [int(v) for v in psi]
+            if len(psi) != self.L:
+                raise ValueError("need one psi per limb")
+            arr = (C.c_uint32 * self.L)(*psi)
+            _ck(lib().agx_create_tables(C.byref(self._h), C.byref(p), C.cast(arr, _u32p), device), "agx_create_tables")
+
+    def set_tables(self, limb: int, roots, precons=None, inverse: bool = False):
+        """Replace one limb's forward / inverse table by the caller's, in the reference's order (ntt.cpp:298-300)."""
+        r = np.ascontiguousarray(roots, dtype=np.uint32)
+        if r.size != self.n:
+            raise ValueError("need n table entries")
+        pp = None
+        if precons is not None:
+            pc = np.ascontiguousarray(precons, dtype=np.uint32)
+            if pc.size != self.n:
+                raise ValueError("need n table entries")
+            pp = pc.ctypes.data_as(_u32p)
+        _ck(lib().agx_set_tables(self._h, limb, int(inverse), r.ctypes.data_as(_u32p), pp), "agx_set_tables")
+
+    def measure_butterfly_peak(self, kind: int = 0, threads_per_sm: int = 1024):
+        """(butterflies per clock per SM, implied SM MHz) of the butterfly instruction stream alone on this GPU."""
+        v, mhz = C.c_double(), C.c_double()
+        _ck(lib().agx_measure_butterfly_peak(self._h, kind, threads_per_sm, C.byref(v), C.byref(mhz)),
+            "agx_measure_butterfly_peak")
+        return v.value, mhz.value
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -265,13 +297,28 @@ class RefPipeline:
     def ntt_input_kernel(self, in1, in2, modulus, twiddles, precons, num_frames: int):
         N = len(twiddles)
         arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (in1, in2, modulus, twiddles, precons)]
+        # agx_ref_input takes bare pointers: the buffer-size contract of ntt_input_kernel (main.cpp:26-37) is checked here
+        if len(arrs[4]) != N or len(arrs[2]) < 1 or len(arrs[0]) < N * num_frames or len(arrs[1]) < N * num_frames:
+            raise ValueError("buffer sizes do not describe numFrames x N")
+        self._n = N
+        self._check_out()
         self._keep += arrs
         _ck(lib().agx_ref_input(self._h, N, *[self._p(a) for a in arrs], num_frames), "agx_ref_input")
 
     def fwd_ntt_kernel(self, compute_unit: int = 0):
         _ck(lib().agx_ref_fwd(self._h, compute_unit), "agx_ref_fwd")
 
+    def _check_out(self):
+        if getattr(self, "_n", 0) and getattr(self, "_out", None) is not None:
+            if self._out[0] < self._out[1] * self._n:
+                self._out = None
+                raise ValueError("out is smaller than numFrames x N")
+
     def ntt_output_kernel(self, out: np.ndarray, num_frames: int):
+        if num_frames < 0:
+            raise ValueError("negative numFrames")
+        self._out = (out.size, num_frames)
+        self._check_out()
         self._keep.append(out)
         _ck(lib().agx_ref_output(self._h, self._p(out), num_frames), "agx_ref_output")
 
@@ -280,6 +327,14 @@ class RefPipeline:
             _ck(lib().agx_wait(self._h), "agx_wait")
         finally:
             self._keep.clear()
+            self._n, self._out = 0, None
+
+    def fwd_dev(self, N: int, d_in, d_in2, d_out, modulus: int, d_tw, d_pre, frames: int, stream=None):
+        """agx_ref_fwd_dev on torch CUDA int64 tensors (or raw device addresses)."""
+        def ptr(t):
+            return t if isinstance(t, int) else t.data_ptr()
+        _ck(lib().agx_ref_fwd_dev(self._h, N, ptr(d_in), ptr(d_in2), ptr(d_out), modulus, ptr(d_tw), ptr(d_pre), frames,
+                                  _stream_ptr(stream)), "agx_ref_fwd_dev")
 
     def launch_count(self) -> int:
         v = C.c_uint64()

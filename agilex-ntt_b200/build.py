@@ -58,21 +58,9 @@ def build_lib(force: bool = False) -> str:
 
 
 def build_tools(force: bool = False) -> dict[str, str]:
-    """Stand-alone binaries: instruction microbenchmark, kernel-variant bench, main.cpp-shaped compat driver."""
+    """Stand-alone binaries: the main.cpp-shaped compat driver, the reference's own main.cpp, the C99 example."""
     os.makedirs(BINDIR, exist_ok=True)
     out = {}
-    mb = os.path.join(BINDIR, "agx_microbench")
-    src = os.path.join(CSRC, "agx_microbench.cu")
-    if os.path.exists(src) and (force or _stale(mb, [src] + _sources(CSRC, (".cuh",)))):
-        _run([nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-o", mb, src])
-    if os.path.exists(mb):
-        out["microbench"] = mb
-    tmb = os.path.join(BINDIR, "agx_tmem_microbench")
-    tsrc = os.path.join(CSRC, "agx_tmem_microbench.cu")
-    if os.path.exists(tsrc) and (force or _stale(tmb, [tsrc] + _sources(CSRC, (".cuh",)))):
-        _run([nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-o", tmb, tsrc])
-    if os.path.exists(tmb):
-        out["tmem_microbench"] = tmb
     drv_src = os.path.join(HOST, "main_compat.cpp")
     drv = os.path.join(BINDIR, "agx_main_compat")
     if os.path.exists(drv_src):

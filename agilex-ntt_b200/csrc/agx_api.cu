@@ -5,14 +5,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "agx_ntt_kernels.cuh"
-#include "agx_ntt_pers.cuh"
-#include "agx_ntt_tm.cuh"
+#include "agx_diag.cuh"
 #include "agx_tables.h"
 
 using namespace agx;
@@ -63,15 +63,13 @@ struct agx_ctx {
     bool has_parms = false;
     uint32_t n = 0, logn = 0, L = 0;
     int le = 0;                                    // 0 = generic kernel
-    unsigned grid_fwd = 0, grid_inv = 0;           // persistent kernels: resident CTAs on this device (multiple of L)
-    std::vector<uint32_t> q, psi;
+    std::vector<uint32_t> q, psi, n_inv;
     uint2 *d_nat_fwd = nullptr, *d_nat_inv = nullptr;      // natural order, ntt.cpp:298-300 (agx_get_tables)
     uint2 *d_tw_fwd = nullptr, *d_tw_inv = nullptr;        // kernel order (natural, with n^-1 in inverse entry 0, when le == 0)
     uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
     LimbConst lc0 = {};                                    // limb 0, passed by value in the kernel parameters
     unsigned long long *d_sum = nullptr;
-    unsigned long long *d_trace = nullptr;                 // AGX_TRACE builds: phase timestamps of sampled CTAs
     uint64_t launches = 0;
     // TMA tensor maps over result buffers (forward kernels store through cp.async.bulk.tensor): the encoder entry
     // point of the driver, and the maps of the most recently used (pointer, polynomial count) pairs
@@ -94,19 +92,40 @@ int select_le(uint32_t logn) {
     }
 }
 
-int set_device(const agx_ctx *c) { CK(cudaSetDevice(c->device)); return AGX_OK; }
+// Every entry point makes the context's device current for its own duration and puts the caller's current device
+// back on return (a library call must not retarget the caller's later CUDA / torch work).
+class DeviceGuard {
+    int prev_ = -1;
+    cudaError_t err_ = cudaSuccess;
+public:
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev_) != cudaSuccess) { cudaGetLastError(); prev_ = -1; }
+        if (prev_ != device) err_ = cudaSetDevice(device); else prev_ = -1;
+    }
+    ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+    int error() const { return (int)err_; }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define AGX_ON_DEVICE(c)                    \
+    DeviceGuard guard__((c)->device);       \
+    if (guard__.error()) return guard__.error()
 
 // Per-limb scalars on the host (psi search, inverses, Barrett constants); the n-entry tables themselves are
 // computed on the device by gen_tables_kernel.
-int build_tables(agx_ctx *c) {
+int build_tables(agx_ctx *c, const uint32_t *psi_in) {
     const uint32_t n = c->n, L = c->L;
     const size_t entries = (size_t)L * n;
     std::vector<LimbConst> lc(L);
     std::vector<LimbGen> lg(L);
     for (uint32_t l = 0; l < L; l++) {
         const uint32_t q = c->q[l];
-        const uint32_t psi = minimal_psi(n, q);
+        uint32_t psi = minimal_psi(n, q);                                 // also validates q (prime, < 2^30, = 1 mod 2n)
         if (!psi) return AGX_E_INVALID;
+        if (psi_in) {                                                     // the caller's root: must be a primitive 2n-th root
+            psi = psi_in[l];
+            if (psi == 0 || psi >= q || powmod_u64(psi, n, q) != q - 1) return AGX_E_INVALID;
+        }
         c->psi[l] = psi;
         lg[l] = LimbGen{q, psi, (uint32_t)powmod_u64(psi, q - 2, q), (uint32_t)powmod_u64(n, q - 2, q)};
         int k = 0;
@@ -117,16 +136,13 @@ int build_tables(agx_ctx *c) {
         x.bar_mu = (uint32_t)(mu << (31 - k));
         x.bar_sh = (uint32_t)(k - 1);
         x.psi = psi; x.zero = 0;
+        c->n_inv[l] = lg[l].n_inv;
     }
     c->lc0 = lc[0];
     CK(cudaMalloc(&c->d_nat_fwd, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_nat_inv, entries * sizeof(uint2)));
     CK(cudaMalloc(&c->d_lc, lc.size() * sizeof(LimbConst)));
     CK(cudaMalloc(&c->d_sum, sizeof(unsigned long long)));
-#if AGX_TRACE
-    CK(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 16 * 4096));
-    CK(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 16 * 4096));
-#endif
     CK(cudaMalloc(&c->d_tw_fwd, entries * sizeof(uint2)));   // generic sizes: natural order with n^-1 in inverse entry 0
     CK(cudaMalloc(&c->d_tw_inv, entries * sizeof(uint2)));
     if (c->le) {
@@ -152,7 +168,7 @@ int build_tables(agx_ctx *c) {
 }
 
 KParams kparams(const agx_ctx *c) {
-    return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->d_trace, c->lc0};
+    return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->lc0};
 }
 
 enum Op { OP_FWD, OP_INV, OP_MUL };
@@ -183,45 +199,6 @@ const CUtensorMap *result_map(agx_ctx *c, void *ptr, size_t T, uint32_t E, uint3
     return &m.map;
 }
 
-// Build-time switches for the experiment kernels (all 0 in the shipped library, which launches one CTA per polynomial;
-// results of the A/B runs: profiles/r01_experiments.md):
-//   AGX_PERSISTENT=1  agx_ntt_pers.cuh: resident CTAs, TMA / cp.async staging, cluster-launch-control work stealing
-//   AGX_TMEM=1        agx_ntt_tm.cuh:   n = 4096 forward kernel with the coefficients parked in tensor memory
-//   AGX_FWD_TMA=1     one-shot forward kernel whose input arrives by one TMA bulk copy
-#ifndef AGX_TMEM
-#define AGX_TMEM 0
-#endif
-#ifndef AGX_PERSISTENT
-#define AGX_PERSISTENT 0
-#endif
-
-template <int LOGN, int LE>
-int setup_persistent(agx_ctx *c) {
-    using G = Geo<LOGN, LE>;
-    auto kf = ntt_fwd_pers_kernel<LOGN, LE>;
-    auto ki = ntt_inv_pers_kernel<LOGN, LE>;
-    // L1 must keep the row pass's per-thread twiddles (8n bytes per limb) resident: leave the carve-out to the driver
-    // unless told otherwise (AGX_CARVEOUT_FWD / AGX_CARVEOUT_INV = percent of the unified array used as shared memory)
-    if (const char *e = getenv("AGX_CARVEOUT_FWD")) CK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-    if (const char *e = getenv("AGX_CARVEOUT_INV")) CK(cudaFuncSetAttribute(ki, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-    int of = 0, oi = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, kf, G::TPP, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oi, ki, G::TPP, 0));
-    if (of < 1 || oi < 1) return AGX_E_UNSUPPORTED;
-    if (const char *e = getenv("AGX_PERS_CTAS")) {                    // tuning knob: resident CTAs per SM
-        const int v = atoi(e);
-        if (v >= 1) { if (v < of) of = v; if (v < oi) oi = v; }
-    }
-    auto round_l = [&](int occ) {
-        unsigned g = (unsigned)occ * (unsigned)c->sms;
-        g -= g % c->L;
-        return g ? g : c->L;
-    };
-    c->grid_fwd = round_l(of);
-    c->grid_inv = round_l(oi);
-    return AGX_OK;
-}
-
 template <int LOGN, int LE, bool CL>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
     using G = Geo<LOGN, LE>;
@@ -229,15 +206,6 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     const dim3 grid((unsigned)T), block(G::TPP);
     const uint32_t Tu = (uint32_t)T;
     static const CUtensorMap no_map = {};          // kernels instantiated without the TMA store ignore their map
-#if AGX_PERSISTENT
-#if AGX_PERS_SCHED
-    const dim3 gridf = grid, gridi = grid;         // one CTA index per polynomial; resident CTAs steal the pending ones
-#else
-    const dim3 gridf(Tu < c->grid_fwd ? Tu : c->grid_fwd), gridi(Tu < c->grid_inv ? Tu : c->grid_inv);   // T is a multiple of L
-#endif
-#define AGX_FWD(dst, src) ntt_fwd_pers_kernel<LOGN, LE><<<gridf, block, 0, s>>>(dst, src, p, Tu)
-#define AGX_INV(dst) ntt_inv_pers_kernel<LOGN, LE><<<gridi, block, 0, s>>>(dst, p, Tu)
-#else
 #define AGX_FWD(dst, src)                                                                                              \
     do {                                                                                                               \
         if (const CUtensorMap *tm = result_map(c, dst, T, G::E, G::TPP))                                               \
@@ -246,14 +214,8 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
             ntt_fwd_loop_kernel<LOGN, LE, false, CL, false><<<grid, block, 0, s>>>(dst, src, nullptr, p, Tu, no_map);  \
     } while (0)
 #define AGX_INV(dst) ntt_inv_loop_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(dst, p, Tu)
-#endif
-#ifndef AGX_FWD_TMA
-#define AGX_FWD_TMA 0
-#endif
     if (op == OP_FWD) {
-        if constexpr (AGX_FWD_TMA != 0) ntt_fwd_tma_kernel<LOGN, LE, CL><<<grid, block, 0, s>>>(out, out, p, Tu);
-        else if constexpr (AGX_TMEM && LOGN == 12) ntt_fwd_tm_kernel<LOGN, LE, CL><<<(Tu + 1) / 2, 128, 0, s>>>(out, out, p, Tu);
-        else AGX_FWD(out, out);
+        AGX_FWD(out, out);
         c->launches++;
     } else if (op == OP_INV) {
         AGX_INV(out);
@@ -294,21 +256,27 @@ int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const ui
         ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
         c->launches++;
     } else {
-        // generic sizes: out <- NTT(a), tmp <- NTT(b) in a stream-ordered scratch buffer, out <- INTT(out .* tmp);
-        // supported when out does not alias b and a != b
-        if (out == b || a == b) return AGX_E_UNSUPPORTED;
-        const size_t bytes = T * c->n * 4;
+        // generic sizes: out <- NTT(a), tmp <- NTT(b) in a stream-ordered scratch buffer, out <- INTT(out .* tmp).
+        // Every aliasing case of the fast path is served: the product commutes (out == b), squaring needs no scratch.
+        if (out == b && out != a) { const uint32_t *t = a; a = b; b = t; }
+        const size_t bytes = T * c->n * 4, total = T * c->n;
         uint32_t *tmp = nullptr;
-        CK(cudaMallocAsync(&tmp, bytes, s));
-        if (out != a) CK(cudaMemcpyAsync(out, a, bytes, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(tmp, b, bytes, cudaMemcpyDeviceToDevice, s));
-        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
-        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(tmp, c->d_tw_fwd, c->d_lc, c->L, c->logn);
-        const size_t total = T * c->n;
-        pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, tmp, c->d_lc, c->L, c->logn, total);
-        ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
-        c->launches += 4;
-        CK(cudaFreeAsync(tmp, s));
+        cudaError_t e = cudaSuccess;
+        if (out != a) e = cudaMemcpyAsync(out, a, bytes, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess && a != b) {
+            e = cudaMallocAsync(&tmp, bytes, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, b, bytes, cudaMemcpyDeviceToDevice, s);
+        }
+        if (e == cudaSuccess) {
+            ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+            if (tmp) ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(tmp, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+            pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, tmp ? tmp : out, c->d_lc, c->L, c->logn, total);
+            ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
+            c->launches += tmp ? 4 : 3;
+            e = cudaGetLastError();
+        }
+        if (tmp) { const cudaError_t ef = cudaFreeAsync(tmp, s); if (e == cudaSuccess) e = ef; }   // freed on every path
+        return (int)e;
     }
     return (int)cudaGetLastError();
 }
@@ -330,7 +298,7 @@ int check_dev_call(agx_ctx *c, const void *p, size_t B) {
     if (!c || !c->has_parms) return AGX_E_INVALID;
     if (B && !p) return AGX_E_INVALID;
     if (reinterpret_cast<uintptr_t>(p) & 15) return AGX_E_INVALID;   // 16-byte vector accesses and tensor copies
-    return set_device(c);
+    return AGX_OK;
 }
 
 // ------------------------------------------------------------------------------------------- host pipeline
@@ -428,15 +396,24 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
     if (!c || !c->has_parms) return AGX_E_INVALID;
     if (B == 0) return AGX_OK;
     if (!h_a || !h_out || (op == OP_MUL && !h_b)) return AGX_E_INVALID;
-    int rc = set_device(c);
-    if (rc) return rc;
+    AGX_ON_DEVICE(c);
     const bool pin_a = is_pinned(h_a), pin_b = op != OP_MUL || is_pinned(h_b), pin_o = is_pinned(h_out);
-    rc = pipe_prepare(c, op == OP_MUL, !(pin_a && pin_b && pin_o));
+    int rc = pipe_prepare(c, op == OP_MUL, !(pin_a && pin_b && pin_o));
     if (rc) return rc;
     HostPipe &P = c->pipe;
     const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
     const size_t chunk_polys = P.cap / poly_bytes;
     OutDrainer drain(c->device);
+    // One way out: whatever fails, no copy may still be touching the caller's memory when this function returns.
+    auto finish = [&](int code) {
+        for (int k = 0; k < kSlots; k++) {
+            const cudaError_t e = cudaStreamSynchronize(P.stream[k]);
+            if (!code && e != cudaSuccess) code = (int)e;
+        }
+        const int d = drain.finish();
+        return code ? code : d;
+    };
+#define STEP(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) return finish((int)e__); } while (0)
     size_t done = 0;
     for (size_t i = 0; done < B; i++) {
         const int sl = (int)(i % kSlots);
@@ -444,31 +421,26 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
         const size_t off = done * poly_words;
         if (i >= (size_t)kSlots) {                       // slot reuse: its previous chunk must have drained
             if (!pin_o) drain.wait_slot_free(i);
-            else if (!pin_a || !pin_b) CK(cudaEventSynchronize(P.done[sl]));
+            else if (!pin_a || !pin_b) STEP(cudaEventSynchronize(P.done[sl]));
         }
         const uint32_t *src_a = h_a + off;
         if (!pin_a) { memcpy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
-        CK(cudaMemcpyAsync(P.d_a[sl], src_a, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
+        STEP(cudaMemcpyAsync(P.d_a[sl], src_a, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
         if (op == OP_MUL) {
             const uint32_t *src_b = h_b + off;
             if (!pin_b) { memcpy(P.p_in2[sl], src_b, bytes); src_b = P.p_in2[sl]; }
-            CK(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
+            STEP(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
         }
         rc = launch(c, op, P.d_a[sl], P.d_a[sl], P.d_b[sl], cnt, P.stream[sl]);
-        if (rc) {                                        // do not return with copies still touching caller memory
-            for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(P.stream[k]);
-            drain.finish();
-            return rc;
-        }
+        if (rc) return finish(rc);
         uint32_t *dst = h_out + off;
-        CK(cudaMemcpyAsync(pin_o ? dst : P.p_out[sl], P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
-        CK(cudaEventRecord(P.done[sl], P.stream[sl]));
+        STEP(cudaMemcpyAsync(pin_o ? dst : P.p_out[sl], P.d_a[sl], bytes, cudaMemcpyDeviceToHost, P.stream[sl]));
+        STEP(cudaEventRecord(P.done[sl], P.stream[sl]));
         if (!pin_o) drain.submit(i, dst, P.p_out[sl], bytes, P.done[sl]);
         done += cnt;
     }
-    rc = drain.finish();
-    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(P.stream[sl]));
-    return rc;
+#undef STEP
+    return finish(AGX_OK);
 }
 
 void pipe_destroy(HostPipe &P) {
@@ -481,6 +453,40 @@ void pipe_destroy(HostPipe &P) {
         if (P.p_out[i]) cudaFreeHost(P.p_out[i]);
     }
     P = HostPipe{};
+}
+
+// ------------------------------------------------------------------------------- reference-shaped u64 kernels
+
+// The forward transform of `frames` frames resident on the device (frame b: low half from in[b*N ..), high half from
+// in2[b*N + N/2 ..), ntt.cpp:582-591; out must not alias the inputs unless in == in2 == out).
+int ref_launch(agx_ctx *c, uint32_t logn, const uint64_t *d_in, const uint64_t *d_in2, uint64_t *d_out, const uint64_t *d_tw,
+               const uint64_t *d_pre, uint64_t modulus, size_t frames, cudaStream_t st) {
+    const uint32_t N = 1u << logn;
+    const size_t frame_bytes = (size_t)N * 8;
+    static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knob: one-CTA-per-frame radix-2 kernel
+    if (logn >= 10 && !naive) {
+        // register-radix passes over the L2-resident chunk: logN - 4 strided stages in groups of <= 4, then the
+        // last 4 stages on contiguous 16-coefficient runs (with the final reduction)
+        uint32_t s0 = 0, left = logn - 4, passes = (logn - 4 + 3) / 4;   // 11 -> 4,4,3; 10 -> 4,3,3; 9 -> 3,3,3; 6 -> 3,3
+        const uint64_t *src = d_in, *src2 = d_in2;
+        for (; passes; passes--) {
+            const uint32_t ls = (left + passes - 1) / passes;
+            const unsigned blocks = (unsigned)((frames << (logn - ls)) + 255) / 256;
+            if (ls == 4) ref_u64_strided_pass_kernel<4><<<blocks, 256, 0, st>>>(src, src2, d_out, d_tw, d_pre, modulus, logn, s0, (uint32_t)frames);
+            else         ref_u64_strided_pass_kernel<3><<<blocks, 256, 0, st>>>(src, src2, d_out, d_tw, d_pre, modulus, logn, s0, (uint32_t)frames);
+            c->launches++;
+            src = src2 = d_out;
+            s0 += ls; left -= ls;
+        }
+        ref_u64_last_pass_kernel<<<(unsigned)((frames << (logn - 4)) + 127) / 128, 128, 0, st>>>(d_out, d_tw, d_pre, modulus, logn, (uint32_t)frames);
+        c->launches++;
+    } else {
+        const int use_smem = frame_bytes <= (128u << 10);
+        const unsigned threads = N / 2 < 1024 ? (N / 2 < 32 ? 32 : N / 2) : 1024;
+        ref_fwd_u64_kernel<<<(unsigned)frames, threads, use_smem ? frame_bytes : 0, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, use_smem);
+        c->launches++;
+    }
+    return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------- reference-shaped u64 pipeline
@@ -496,8 +502,7 @@ int ref_flush(agx_ctx *c) {
     R.have_in = R.have_fwd = R.have_out = false;
     if (R.out_frames < 0 || (uint32_t)R.out_frames != R.frames) return AGX_E_INVALID;
     if (R.frames == 0) return AGX_OK;
-    int rc = set_device(c);
-    if (rc) return rc;
+    AGX_ON_DEVICE(c);
     if (!R.stream[0]) {
         for (int i = 0; i < kSlots; i++) {
             CK(cudaStreamCreateWithFlags(&R.stream[i], cudaStreamNonBlocking));
@@ -538,16 +543,25 @@ int ref_flush(agx_ctx *c) {
         R.have_stage_out = true;
     }
     const uint64_t modulus = R.mod[0];
+    OutDrainer drain(c->device);
+    // From here on copies touch the caller's buffers.  On any failure: drain every stream and the helper thread before
+    // returning, so that nothing is in flight behind the caller's back; on success the round stays asynchronous and
+    // agx_wait() completes it (R.busy).
+    auto fail = [&](int code) {
+        for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(R.stream[k]);
+        drain.finish();
+        R.busy = false;
+        return code;
+    };
+#define STEP(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((int)e__); } while (0)
+    R.busy = true;
     // tables: once per round (ntt.cpp:119-144 receives them once per mini-batch), the other slots wait for them
-    CK(cudaMemcpyAsync(R.d_tw, R.tw, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
-    CK(cudaMemcpyAsync(R.d_pre, R.pre, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
-    CK(cudaEventRecord(R.tables, R.stream[0]));
-    for (int i = 1; i < kSlots; i++) CK(cudaStreamWaitEvent(R.stream[i], R.tables, 0));
+    STEP(cudaMemcpyAsync(R.d_tw, R.tw, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
+    STEP(cudaMemcpyAsync(R.d_pre, R.pre, frame_bytes, cudaMemcpyHostToDevice, R.stream[0]));
+    STEP(cudaEventRecord(R.tables, R.stream[0]));
+    for (int i = 1; i < kSlots; i++) STEP(cudaStreamWaitEvent(R.stream[i], R.tables, 0));
     uint32_t logn = 0;
     while ((1u << logn) < R.N) logn++;
-    const int use_smem = frame_bytes <= (128u << 10);
-    const unsigned threads = R.N / 2 < 1024 ? (R.N / 2 < 32 ? 32 : R.N / 2) : 1024;
-    OutDrainer drain(c->device);
     size_t done = 0;
     for (size_t i = 0; done < R.frames; i++) {
         const int sl = (int)(i % kSlots);
@@ -556,15 +570,15 @@ int ref_flush(agx_ctx *c) {
         const size_t off = done * N;
         if (i >= (size_t)kSlots) {                                   // staging buffers of this slot are about to be reused
             if (!pin_out) drain.wait_slot_free(i);
-            else if (!pin_in) CK(cudaEventSynchronize(R.done[sl]));
+            else if (!pin_in) STEP(cudaEventSynchronize(R.done[sl]));
         }
         if (pin_in) {
             if (same) {
-                CK(cudaMemcpyAsync(R.d_in[sl], R.in + off, bytes, cudaMemcpyHostToDevice, st));
+                STEP(cudaMemcpyAsync(R.d_in[sl], R.in + off, bytes, cudaMemcpyHostToDevice, st));
             } else {
-                CK(cudaMemcpy2DAsync(R.d_in[sl], frame_bytes, R.in + off, frame_bytes, half_bytes, cnt, cudaMemcpyHostToDevice, st));
-                CK(cudaMemcpy2DAsync(R.d_in[sl] + N / 2, frame_bytes, R.in2 + off + N / 2, frame_bytes, half_bytes, cnt,
-                                     cudaMemcpyHostToDevice, st));
+                STEP(cudaMemcpy2DAsync(R.d_in[sl], frame_bytes, R.in + off, frame_bytes, half_bytes, cnt, cudaMemcpyHostToDevice, st));
+                STEP(cudaMemcpy2DAsync(R.d_in[sl] + N / 2, frame_bytes, R.in2 + off + N / 2, frame_bytes, half_bytes, cnt,
+                                       cudaMemcpyHostToDevice, st));
             }
         } else {
             if (same) {
@@ -575,45 +589,19 @@ int ref_flush(agx_ctx *c) {
                     memcpy(R.p_in[sl] + f * N + N / 2, R.in2 + off + f * N + N / 2, half_bytes);
                 }
             }
-            CK(cudaMemcpyAsync(R.d_in[sl], R.p_in[sl], bytes, cudaMemcpyHostToDevice, st));
+            STEP(cudaMemcpyAsync(R.d_in[sl], R.p_in[sl], bytes, cudaMemcpyHostToDevice, st));
         }
-        static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knob: one-CTA-per-frame radix-2 kernel
-        if (logn >= 10 && !naive) {
-            // register-radix passes over the L2-resident chunk: logN - 4 strided stages in groups of <= 4, then the
-            // last 4 stages on contiguous 16-coefficient runs (with the final reduction)
-            uint32_t s0 = 0, left = logn - 4, passes = (logn - 4 + 3) / 4;   // 11 -> 4,4,3; 10 -> 4,3,3; 9 -> 3,3,3; 6 -> 3,3
-            const uint64_t *src = R.d_in[sl];
-            for (; passes; passes--) {
-                const uint32_t ls = (left + passes - 1) / passes;
-                const unsigned blocks = (unsigned)((cnt << (logn - ls)) + 255) / 256;
-                if (ls == 4) ref_u64_strided_pass_kernel<4><<<blocks, 256, 0, st>>>(src, R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, s0, (uint32_t)cnt);
-                else         ref_u64_strided_pass_kernel<3><<<blocks, 256, 0, st>>>(src, R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, s0, (uint32_t)cnt);
-                c->launches++;
-                src = R.d_out[sl];
-                s0 += ls; left -= ls;
-            }
-            ref_u64_last_pass_kernel<<<(unsigned)((cnt << (logn - 4)) + 127) / 128, 128, 0, st>>>(R.d_out[sl], R.d_tw, R.d_pre, modulus, logn, (uint32_t)cnt);
-            c->launches++;
-        } else {
-            ref_fwd_u64_kernel<<<(unsigned)cnt, threads, use_smem ? frame_bytes : 0, st>>>(R.d_in[sl], R.d_in[sl], R.d_out[sl], R.d_tw,
-                                                                                        R.d_pre, modulus, logn, use_smem);
-            c->launches++;
-        }
-        rc = (int)cudaGetLastError();
-        if (rc) {
-            for (int k = 0; k < kSlots; k++) cudaStreamSynchronize(R.stream[k]);
-            drain.finish();
-            return rc;
-        }
+        const int rc = ref_launch(c, logn, R.d_in[sl], R.d_in[sl], R.d_out[sl], R.d_tw, R.d_pre, modulus, cnt, st);
+        if (rc) return fail(rc);
         uint64_t *dst = R.out + off;
-        CK(cudaMemcpyAsync(pin_out ? dst : R.p_out[sl], R.d_out[sl], bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(R.done[sl], st));
+        STEP(cudaMemcpyAsync(pin_out ? dst : R.p_out[sl], R.d_out[sl], bytes, cudaMemcpyDeviceToHost, st));
+        STEP(cudaEventRecord(R.done[sl], st));
         if (!pin_out) drain.submit(i, dst, R.p_out[sl], bytes, R.done[sl]);
         done += cnt;
     }
-    rc = drain.finish();                                             // pageable results are complete on return
-    R.busy = true;
-    return rc;
+#undef STEP
+    const int rc = drain.finish();                                   // pageable results are complete on return
+    return rc ? fail(rc) : AGX_OK;
 }
 
 }  // namespace
@@ -622,10 +610,14 @@ int ref_flush(agx_ctx *c) {
 
 extern "C" {
 
-int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
+int agx_create(agx_ctx **out, const agx_parms *parms, int device) { return agx_create_tables(out, parms, nullptr, device); }
+
+int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi, int device) {
     if (!out) return AGX_E_INVALID;
     *out = nullptr;
-    CK(cudaSetDevice(device));
+    if (psi && !parms) return AGX_E_INVALID;
+    DeviceGuard guard__(device);
+    if (guard__.error()) return guard__.error();
     CK(cudaFree(0));
     agx_ctx *c = new (std::nothrow) agx_ctx();
     if (!c) return AGX_E_NOMEM;
@@ -658,19 +650,8 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
         c->le = select_le(c->logn);
         c->q.assign(parms->q, parms->q + parms->nlimbs);
         c->psi.resize(c->L);
-        int rc = build_tables(c);
-#if AGX_TMEM
-        // 8 CTAs x 10.8 KB of shared memory per SM must fit the carve-out
-        if (!rc && c->logn == 12) {
-            int pct = 64;
-            if (const char *e = getenv("AGX_TM_CARVEOUT")) pct = atoi(e);
-            rc = (int)cudaFuncSetAttribute(ntt_fwd_tm_kernel<12, 6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            if (!rc) rc = (int)cudaFuncSetAttribute(ntt_fwd_tm_kernel<12, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
-#endif
-#if AGX_PERSISTENT
-        if (!rc && c->le) rc = c->logn == 12 ? setup_persistent<12, 6>(c) : c->logn == 11 ? setup_persistent<11, 6>(c) : setup_persistent<10, 5>(c);
-#endif
+        c->n_inv.resize(c->L);
+        int rc = build_tables(c, psi);
         if (rc) { agx_destroy(c); return rc; }
     }
     *out = c;
@@ -679,22 +660,24 @@ int agx_create(agx_ctx **out, const agx_parms *parms, int device) {
 
 int agx_destroy(agx_ctx *c) {
     if (!c) return AGX_OK;
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
-    pipe_destroy(c->pipe);
-    RefState &R = c->ref;
-    for (int i = 0; i < kSlots; i++) {
-        cudaFree(R.d_in[i]); cudaFree(R.d_out[i]);
-        if (R.p_in[i]) cudaFreeHost(R.p_in[i]);
-        if (R.p_out[i]) cudaFreeHost(R.p_out[i]);
-        if (R.stream[i]) cudaStreamDestroy(R.stream[i]);
-        if (R.done[i]) cudaEventDestroy(R.done[i]);
+    {
+        DeviceGuard guard__(c->device);
+        cudaDeviceSynchronize();
+        pipe_destroy(c->pipe);
+        RefState &R = c->ref;
+        for (int i = 0; i < kSlots; i++) {
+            cudaFree(R.d_in[i]); cudaFree(R.d_out[i]);
+            if (R.p_in[i]) cudaFreeHost(R.p_in[i]);
+            if (R.p_out[i]) cudaFreeHost(R.p_out[i]);
+            if (R.stream[i]) cudaStreamDestroy(R.stream[i]);
+            if (R.done[i]) cudaEventDestroy(R.done[i]);
+        }
+        if (R.tables) cudaEventDestroy(R.tables);
+        cudaFree(R.d_tw); cudaFree(R.d_pre);
+        cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_nat_fwd); cudaFree(c->d_nat_inv);
+        cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
+        cudaFree(c->d_lc); cudaFree(c->d_sum);
     }
-    if (R.tables) cudaEventDestroy(R.tables);
-    cudaFree(R.d_tw); cudaFree(R.d_pre);
-    cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_nat_fwd); cudaFree(c->d_nat_inv);
-    cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
-    cudaFree(c->d_lc); cudaFree(c->d_sum); cudaFree(c->d_trace);
     delete c;
     return AGX_OK;
 }
@@ -707,7 +690,7 @@ int agx_get_psi(const agx_ctx *c, uint32_t limb, uint32_t *psi) {
 
 int agx_get_tables(const agx_ctx *c, uint32_t limb, int inverse, uint32_t *roots, uint32_t *precons) {
     if (!c || !c->has_parms || limb >= c->L || !roots || !precons) return AGX_E_INVALID;
-    CK(cudaSetDevice(c->device));
+    AGX_ON_DEVICE(c);
     std::vector<uint2> t(c->n);
     CK(cudaMemcpy(t.data(), (inverse ? c->d_nat_inv : c->d_nat_fwd) + (size_t)limb * c->n, (size_t)c->n * sizeof(uint2),
                   cudaMemcpyDeviceToHost));
@@ -715,14 +698,60 @@ int agx_get_tables(const agx_ctx *c, uint32_t limb, int inverse, uint32_t *roots
     return AGX_OK;
 }
 
+int agx_set_tables(agx_ctx *c, uint32_t limb, int inverse, const uint32_t *roots, const uint32_t *precons) {
+    if (!c || !c->has_parms || limb >= c->L || !roots) return AGX_E_INVALID;
+    AGX_ON_DEVICE(c);
+    const uint32_t n = c->n;
+    const size_t base = (size_t)limb * n;
+    // the new tables are built beside the live ones and swapped in only when the caller's table proved consistent
+    uint32_t *d_in = nullptr;
+    uint2 *d_new = nullptr;
+    unsigned *d_bad = nullptr;
+    const size_t sets = c->le ? 3 : 2;
+    cudaError_t e = cudaMalloc(&d_in, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_new, sets * n * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(d_bad, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(d_new, 0, sets * n * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, roots, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && precons) e = cudaMemcpy(d_in + n, precons, (size_t)n * 4, cudaMemcpyHostToDevice);
+    unsigned bad = 1;
+    if (e == cudaSuccess) {
+        const TableSet t{d_new, d_new + n, c->le ? d_new + 2 * (size_t)n : nullptr};
+        relayout_tables_kernel<<<(n + 255) / 256, 256>>>(t, d_in, precons ? d_in + n : nullptr, inverse != 0, c->q[limb],
+                                                         c->n_inv[limb], c->logn, c->le, d_bad);
+        c->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && bad == 0) {
+        const size_t bytes = (size_t)n * sizeof(uint2);
+        e = cudaMemcpy((inverse ? c->d_nat_inv : c->d_nat_fwd) + base, d_new, bytes, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy((inverse ? c->d_tw_inv : c->d_tw_fwd) + base, d_new + n, bytes, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess && c->le)
+            e = cudaMemcpy((inverse ? c->d_twc_inv : c->d_twc_fwd) + base, d_new + 2 * (size_t)n, bytes, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess && !inverse) {                               // psi = roots[n/2] (bitrev(n/2) = 1)
+            c->psi[limb] = roots[n / 2];
+            if (limb == 0) c->lc0.psi = roots[n / 2];
+        }
+    }
+    cudaFree(d_in); cudaFree(d_new); cudaFree(d_bad);
+    if (e != cudaSuccess) return (int)e;
+    return bad ? AGX_E_INVALID : AGX_OK;
+}
+
 int agx_ntt_fwd(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
     int rc = check_dev_call(c, d, B);
-    return rc ? rc : launch(c, OP_FWD, d, d, nullptr, B, (cudaStream_t)stream);
+    if (rc) return rc;
+    AGX_ON_DEVICE(c);
+    return launch(c, OP_FWD, d, d, nullptr, B, (cudaStream_t)stream);
 }
 
 int agx_ntt_inv(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
     int rc = check_dev_call(c, d, B);
-    return rc ? rc : launch(c, OP_INV, d, d, nullptr, B, (cudaStream_t)stream);
+    if (rc) return rc;
+    AGX_ON_DEVICE(c);
+    return launch(c, OP_INV, d, d, nullptr, B, (cudaStream_t)stream);
 }
 
 int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db, size_t B, void *stream) {
@@ -730,6 +759,7 @@ int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db
     if (rc) return rc;
     if (B && (!da || !db)) return AGX_E_INVALID;
     if ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db)) & 15) return AGX_E_INVALID;
+    AGX_ON_DEVICE(c);
     return launch(c, OP_MUL, dc, da, db, B, (cudaStream_t)stream);
 }
 
@@ -739,6 +769,8 @@ int agx_elementwise(agx_ctx *c, int op, uint32_t *dc, const uint32_t *da, const 
     if (op < 0 || op > 3) return AGX_E_INVALID;
     if (B == 0) return AGX_OK;
     if (!da || !db) return AGX_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db)) & 15) return AGX_E_INVALID;   // read as uint4
+    AGX_ON_DEVICE(c);
     const size_t total4 = B * c->L * c->n / 4;
     size_t blocks = (total4 + 255) / 256;
     if (blocks > (size_t)c->sms * 16) blocks = (size_t)c->sms * 16;
@@ -760,6 +792,7 @@ int agx_bitrev(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
     if (rc || B == 0) return rc;
     const size_t T = B * c->L;
     if (T > 0x7fffffffull) return AGX_E_INVALID;
+    AGX_ON_DEVICE(c);
     const unsigned threads = c->n / 4 < 256 ? (c->n / 4 < 32 ? 32 : c->n / 4) : 256;
     bitrev_rows_kernel<<<(unsigned)T, threads, (size_t)c->n * 4, (cudaStream_t)stream>>>(d, c->logn);
     c->launches++;
@@ -789,6 +822,7 @@ int agx_host_free(void *p) {
 int agx_fill_synthetic(agx_ctx *c, uint32_t *d, size_t B, uint64_t seed, size_t first_poly, void *stream) {
     int rc = check_dev_call(c, d, B);
     if (rc || B == 0) return rc;
+    AGX_ON_DEVICE(c);
     const size_t total = B * c->L * c->n;
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -800,8 +834,7 @@ int agx_fill_synthetic(agx_ctx *c, uint32_t *d, size_t B, uint64_t seed, size_t 
 
 int agx_checksum(agx_ctx *c, const uint32_t *d, size_t count, size_t first_index, uint64_t *h_sum, void *stream) {
     if (!c || !c->has_parms || !h_sum || (count && !d)) return AGX_E_INVALID;
-    int rc = set_device(c);
-    if (rc) return rc;
+    AGX_ON_DEVICE(c);
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), s));
     if (count) {
@@ -853,11 +886,73 @@ int agx_wait(agx_ctx *c) {
         return AGX_E_STATE;
     }
     if (R.busy) {
-        CK(cudaSetDevice(c->device));
-        for (int i = 0; i < kSlots; i++) CK(cudaStreamSynchronize(R.stream[i]));
+        AGX_ON_DEVICE(c);
         R.busy = false;
+        int rc = AGX_OK;
+        for (int i = 0; i < kSlots; i++) {                // every stream, even after a failure on an earlier one
+            const cudaError_t e = cudaStreamSynchronize(R.stream[i]);
+            if (!rc && e != cudaSuccess) rc = (int)e;
+        }
+        return rc;
     }
     return AGX_OK;
+}
+
+int agx_ref_fwd_dev(agx_ctx *c, uint32_t N, const uint64_t *d_in, const uint64_t *d_in2, uint64_t *d_out, uint64_t modulus,
+                    const uint64_t *d_twiddles, const uint64_t *d_precon_twiddles, uint32_t numFrames, void *stream) {
+    if (!c || !d_in || !d_in2 || !d_out || !d_twiddles || !d_precon_twiddles) return AGX_E_INVALID;
+    if (N < 4 || N > 32768 || (N & (N - 1))) return AGX_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_in2) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+        return AGX_E_INVALID;
+    // the passes work in place in d_out after the first one, so an input that overlaps it is only safe when it IS it
+    if ((d_in != d_out || d_in2 != d_out) && (d_in == d_out || d_in2 == d_out)) return AGX_E_INVALID;
+    if (numFrames == 0) return AGX_OK;
+    AGX_ON_DEVICE(c);
+    uint32_t logn = 0;
+    while ((1u << logn) < N) logn++;
+    return ref_launch(c, logn, d_in, d_in2, d_out, d_twiddles, d_precon_twiddles, modulus, numFrames, (cudaStream_t)stream);
+}
+
+int agx_measure_butterfly_peak(agx_ctx *c, int kind, int threads_per_sm, double *per_clk_per_sm, double *sm_mhz) {
+    if (!c || !per_clk_per_sm || kind < 0 || kind > 1) return AGX_E_INVALID;
+    if (threads_per_sm < 128 || threads_per_sm > 1024 || threads_per_sm % 128) return AGX_E_INVALID;
+    AGX_ON_DEVICE(c);
+    uint32_t *d_out = nullptr;
+    long long *d_cyc = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const int sms = c->sms;
+    const uint32_t q = 1053818881u;
+    const LimbConst lc{q, 2 * q, 0u - q, 0u - 2 * q, 0, 29, 0, 0};
+    const uint64_t q64 = 1152921504606584833ull;
+    cudaError_t e = cudaMalloc(&d_out, sizeof(uint32_t) * sms * 1024);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cyc, sizeof(long long) * sms);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float ms = 0;
+    std::vector<long long> cyc(sms);
+    if (e == cudaSuccess) {
+        for (int rep = 0; rep < 2; rep++) {                // first launch warms the clocks and the instruction cache
+            if (rep == 1) cudaEventRecord(e0, 0);
+            if (kind == 0) diag_bfly_kernel<0><<<sms, threads_per_sm>>>(d_out, d_cyc, 12345u, lc, q64);
+            else diag_bfly_kernel<1><<<sms, threads_per_sm>>>(d_out, d_cyc, 12345u, lc, q64);
+            c->launches++;
+        }
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess) e = cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) {
+        std::sort(cyc.begin(), cyc.end());
+        const double med = (double)cyc[sms / 2];
+        *per_clk_per_sm = (double)kDiagIters * kDiagUnroll * kDiagChains * threads_per_sm / med;
+        if (sm_mhz) *sm_mhz = ms > 0 ? med / (ms * 1e3) : 0.0;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_out); cudaFree(d_cyc);
+    return (int)e;
 }
 
 const char *agx_error_string(int code) {
@@ -874,13 +969,6 @@ const char *agx_error_string(int code) {
 int agx_launch_count(const agx_ctx *c, uint64_t *count) {
     if (!c || !count) return AGX_E_INVALID;
     *count = c->launches;
-    return AGX_OK;
-}
-
-// AGX_TRACE builds only (deliberately not in the public header): phase timestamps of the last forward launch
-int agx_debug_trace(const agx_ctx *c, unsigned long long *out, size_t count) {
-    if (!c || !c->d_trace || !out || count > 16 * 4096) return AGX_E_UNSUPPORTED;
-    CK(cudaMemcpy(out, c->d_trace, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return AGX_OK;
 }
 

@@ -41,7 +41,6 @@ struct KParams {
     const uint2 *twc_inv;
     const LimbConst *lc;     // [L]
     uint32_t L;
-    unsigned long long *trace;   // AGX_TRACE builds only: per-CTA phase timestamps (profiles/trace_phases.py)
     LimbConst c0;                // limb 0's constants by value: kernel parameters live in the constant bank, so the
                                  // butterfly's q / 2q / -q / -2q / 0 operands cost no register-file read when L == 1
 };
@@ -52,25 +51,6 @@ struct KParams {
     LimbConst limb_consts_;                     \
     if constexpr (!(CL)) limb_consts_ = (p).lc[limb]; \
     const LimbConst &c = (CL) ? (p).c0 : limb_consts_
-
-// Timing-experiment switches (never set in the shipped library):
-//   AGX_TRACE=1   thread 0 of every 64th CTA stamps clock64() at phase boundaries of the forward kernel
-//   AGX_ABLATE=k  bit0 no global loads, bit1 no stores/staging, bit2 no smem transpose, bit4 no final reduction
-//                 (results of these experiments: profiles/r01_experiments.md)
-#ifndef AGX_TRACE
-#define AGX_TRACE 0
-#endif
-#ifndef AGX_ABLATE
-#define AGX_ABLATE 0
-#endif
-#ifndef AGX_DIRECT_STORE
-#define AGX_DIRECT_STORE 0
-#endif
-#if AGX_TRACE
-#define AGX_STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x % 64) == 5) p.trace[(blockIdx.x / 64) * 16 + (i)] = clock64(); } while (0)
-#else
-#define AGX_STAMP(i) do { } while (0)
-#endif
 
 template <int LOGN, int LE>
 struct Geo {
@@ -471,50 +451,27 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
     uint32_t *g = dst + (size_t)poly * G::N;
 
     uint32_t x[G::E];
-    AGX_STAMP(0);
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         PassAddr a;
         if (pass == 0) {                             // column pass: x[k] = poly[tid + TPP*k], stages 0..LE-1
             a = pass_addr<LOGN, LE>(twc, 0u);
-#if AGX_ABLATE & 1
-#pragma unroll
-            for (int k = 0; k < G::E; k++) x[k] = tid * 977u + k * 131071u + poly;
-#else
 #pragma unroll
             for (int k = 0; k < G::E; k++) x[k] = ld_stream(gs + tid + G::TPP * k);
-#endif
             prefetch_ahead<LOGN, G::TPP>(gs, poly, T, tid);
         } else {                                     // row pass: x[j] = poly[E*tid + j], stages LE..logn-1
             a = pass_addr<LOGN, LE>(tw, tid);
-#if !(AGX_ABLATE & 4)
             lds_row<LOGN, LE>(sm, x, tid);
-#endif
         }
         if (G::LT == LE || pass == 0) ct_stage<LOGN, LE, 0>(x, a, c);
-        AGX_STAMP(1 + 7 * pass);                     // stage 0 done (pass 0: includes the wait for the global loads)
-#if AGX_TRACE
-        ct_stage<LOGN, LE, 1>(x, a, c); AGX_STAMP(2 + 7 * pass);
-        ct_stage<LOGN, LE, 2>(x, a, c); AGX_STAMP(3 + 7 * pass);
-        ct_stage<LOGN, LE, 3>(x, a, c); AGX_STAMP(4 + 7 * pass);
-        ct_stage<LOGN, LE, 4>(x, a, c); AGX_STAMP(5 + 7 * pass);
-        if constexpr (LE > 5) ct_stage<LOGN, LE, LE - 1>(x, a, c);
-        AGX_STAMP(6 + 7 * pass);
-#else
         ct_stages_from<LOGN, LE, 1>(x, a, c);
-#endif
         if (pass == 0) {
-#if !(AGX_ABLATE & 4)
             sts_columns<LOGN, LE>(reinterpret_cast<uint32_t *>(sm), x, tid);
-#endif
             poly_sync<G::TPP>();
-            AGX_STAMP(7);
         }
     }
-#if !(AGX_ABLATE & 16)
 #pragma unroll
     for (int j = 0; j < G::E; j++) x[j] = reduce4q(x[j], c);
-#endif
     if constexpr (MUL) {
         poly_sync<G::TPP>();                         // every thread has read its row of the transpose buffer
         global_to_smem<LOGN, LE>(sm, mul + (size_t)poly * G::N, tid);
@@ -528,19 +485,6 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
             x[4 * cc + 3] = csub(barrett_mul_lazy(mv.w, x[4 * cc + 3], c), c.neg2q);
         }
     }
-#if AGX_ABLATE & 2
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < G::E; j++) acc ^= x[j];
-    if (acc == 0x12345678u) g[tid] = acc;            // ablation: keep the math alive, store (almost) nothing
-#else
-#if AGX_DIRECT_STORE
-    {   // experiment: rows straight from registers, 16 bytes per lane at a 4*E-byte stride (partial-sector writes)
-        uint4 *g4 = reinterpret_cast<uint4 *>(g) + tid * G::CPR;
-#pragma unroll
-        for (int cc = 0; cc < G::CPR; cc++) __stcs(g4 + cc, make_uint4(x[4 * cc], x[4 * cc + 1], x[4 * cc + 2], x[4 * cc + 3]));
-    }
-#else
     if constexpr (TMA) {
         poly_sync<G::TPP>();                         // the dense tiles overlap other threads' rows of the padded image
         sts_row_swz<LOGN, LE>(sm, x, tid);
@@ -550,12 +494,8 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
     } else {
         sts_row<LOGN, LE>(sm, x, tid);               // own row only: no barrier needed before
         poly_sync<G::TPP>();
-        AGX_STAMP(14);
         smem_to_global<LOGN, LE>(sm, g, tid);
-        AGX_STAMP(15);
     }
-#endif
-#endif
 }
 
 template <int LOGN, int LE, bool CL>
@@ -603,7 +543,7 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
 // transformed.  HBM traffic: 3 * n * 4 bytes per product.
 template <int LOGN, int LE, bool CL>
 __global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
-polymul_loop_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, KParams p) {
+polymul_loop_kernel(uint32_t *out, const uint32_t *a, const uint32_t *b, KParams p) {   // out may alias a and/or b
     using G = Geo<LOGN, LE>;
     __shared__ uint4 sm[G::SMEM_CHUNKS];
     __shared__ uint4 park[G::SMEM_CHUNKS];
@@ -860,7 +800,7 @@ __device__ __forceinline__ void ref_stages_u64(uint64_t (&x)[1 << LS], const uin
 }
 
 template <int LS>
-__global__ void __launch_bounds__(256) ref_u64_strided_pass_kernel(const uint64_t *src, uint64_t *dst,
+__global__ void __launch_bounds__(256) ref_u64_strided_pass_kernel(const uint64_t *src, const uint64_t *src2, uint64_t *dst,
                                                                    const uint64_t *__restrict__ roots,
                                                                    const uint64_t *__restrict__ precons, uint64_t q,
                                                                    uint32_t logn, uint32_t s0, uint32_t frames) {
@@ -870,10 +810,14 @@ __global__ void __launch_bounds__(256) ref_u64_strided_pass_kernel(const uint64_
     if (frame >= frames) return;
     const uint32_t lo_bits = logn - s0 - LS;
     const uint32_t p_lo = tidx & ((1u << lo_bits) - 1), p_hi = tidx >> lo_bits;
-    const size_t base = ((size_t)frame << logn) + ((size_t)p_hi << (logn - s0)) + p_lo;
+    const uint32_t pos = (p_hi << (logn - s0)) + p_lo;                    // position of element k = 0 inside the frame
+    const size_t base = ((size_t)frame << logn) + pos;
     uint64_t x[E];
 #pragma unroll
-    for (int k = 0; k < E; k++) x[k] = src[base + ((size_t)k << lo_bits)];
+    for (int k = 0; k < E; k++) {                                         // high half of a frame comes from src2 (ntt.cpp:587-589)
+        const uint64_t *s = ((pos + ((uint32_t)k << lo_bits)) >> (logn - 1)) ? src2 : src;
+        x[k] = s[base + ((size_t)k << lo_bits)];
+    }
     ref_stages_u64<LS>(x, roots, precons, s0, p_hi, q);
 #pragma unroll
     for (int k = 0; k < E; k++) dst[base + ((size_t)k << lo_bits)] = x[k];
@@ -940,7 +884,42 @@ __device__ __forceinline__ uint32_t mulmod_dev(uint32_t a, uint32_t b, uint32_t 
     return (uint32_t)(((uint64_t)a * b) % q);
 }
 
-// le == 0: generic sizes, kernel order == natural order and no column tables
+// Places entry k (value r = base^bitrev(k)) of one limb's table into every layout the kernels read:
+// natural order, kernel order (tw_pos) and -- for k < E -- the column pass's slots; inverse tables get n^-1 folded in.
+// le == 0: generic sizes, kernel order == natural order and no column tables.
+struct TableSet {
+    uint2 *nat, *tw, *twc;      // one limb, one direction
+};
+
+__device__ __forceinline__ uint2 shoup_pair(uint32_t w, uint32_t q) { return make_uint2(w, (uint32_t)(((uint64_t)w << 32) / q)); }
+
+__device__ __forceinline__ void place_table_entry(const TableSet &t, uint32_t k, uint32_t r, bool inverse, uint32_t q,
+                                                  uint32_t n_inv, uint32_t logn, int le) {
+    const uint2 natural = shoup_pair(r, q);
+    t.nat[k] = natural;
+    uint32_t w = r;
+    if (inverse && k == 0) w = n_inv;                                    // unused slot carries n^-1
+    if (inverse && k == 1 && le) w = mulmod_dev(r, n_inv, q);            // last GS stage folds n^-1 (two-pass kernels)
+    uint32_t pos = k;
+    if (le && k >= (1u << le)) {
+        const int s = 31 - __clz(k), lt = (int)logn - le;
+        const uint32_t c = 1u << (s - lt), rr = k - (1u << s), tpp = 1u << lt;
+        const uint32_t T = rr / c, kk = rr % c;
+        pos = c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * tpp + T) * 2 + (kk & 1);   // = tw_pos<LOGN,LE>(s, T, kk)
+    }
+    t.tw[pos] = shoup_pair(w, q);
+    if (le && k >= 1 && k < (1u << le)) {   // column pass: local stage j, group gq sits where the row pass of thread 0 looks
+        const int j = 31 - __clz(k), lt = (int)logn - le;
+        const uint32_t gq = k - (1u << j), tpp = 1u << lt;
+        const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
+        uint2 cval = natural;
+        if (inverse && j >= 1 && j <= kInvFold) cval = shoup_pair(mulmod_dev(r, n_inv, q), q);   // variant A carries n^-1
+        t.twc[cpos] = cval;
+        if (inverse && j >= 1) t.twc[cpos + 2] = natural;                 // variant B: one 16-byte slot further
+    }
+}
+
+// Tables from psi: one thread per (direction, limb, k).
 __global__ void __launch_bounds__(256) gen_tables_kernel(uint2 *__restrict__ nat_fwd, uint2 *__restrict__ nat_inv,
                                                          uint2 *__restrict__ tw_fwd, uint2 *__restrict__ tw_inv,
                                                          uint2 *__restrict__ twc_fwd, uint2 *__restrict__ twc_inv,
@@ -958,32 +937,36 @@ __global__ void __launch_bounds__(256) gen_tables_kernel(uint2 *__restrict__ nat
         b = mulmod_dev(b, b, g.q);
     }
     const size_t base = (size_t)limb * n;
-    const uint2 natural = make_uint2(r, (uint32_t)(((uint64_t)r << 32) / g.q));
-    (inverse ? nat_inv : nat_fwd)[base + k] = natural;
-    uint32_t w = r;
-    if (inverse && k == 0) w = g.n_inv;                                  // unused slot carries n^-1
-    if (inverse && k == 1 && le) w = mulmod_dev(r, g.n_inv, g.q);        // last GS stage folds n^-1 (two-pass kernels)
-    const uint2 entry = make_uint2(w, (uint32_t)(((uint64_t)w << 32) / g.q));
-    uint32_t pos = k;
-    if (le && k >= (1u << le)) {
-        const int s = 31 - __clz(k), lt = (int)logn - le;
-        const uint32_t c = 1u << (s - lt), rr = k - (1u << s), tpp = 1u << lt;
-        const uint32_t T = rr / c, kk = rr % c;
-        pos = c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * tpp + T) * 2 + (kk & 1);   // = tw_pos<LOGN,LE>(s, T, kk)
-    }
-    (inverse ? tw_inv : tw_fwd)[base + pos] = entry;
-    if (le && k >= 1 && k < (1u << le)) {   // column pass: local stage j, group gq sits where the row pass of thread 0 looks
-        const int j = 31 - __clz(k), lt = (int)logn - le;
-        const uint32_t gq = k - (1u << j), tpp = 1u << lt;
-        const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
-        uint2 cval = natural;
-        if (inverse && j >= 1 && j <= kInvFold) {                         // variant A of the folded stages carries n^-1
-            const uint32_t ws = mulmod_dev(r, g.n_inv, g.q);
-            cval = make_uint2(ws, (uint32_t)(((uint64_t)ws << 32) / g.q));
+    const TableSet t{(inverse ? nat_inv : nat_fwd) + base, (inverse ? tw_inv : tw_fwd) + base,
+                     le ? (inverse ? twc_inv : twc_fwd) + base : nullptr};
+    place_table_entry(t, k, r, inverse, g.q, g.n_inv, logn, le);
+}
+
+// Tables handed in by the caller in the reference's order (ntt.cpp:298-300: entry m + i = twiddle of group i in the
+// stage with m groups; include/kernel/ntt.h:35-41, main.cpp:36-37,46-55 hand such buffers to the loader): checked for
+// consistency and re-laid-out for the kernels.  One thread per k.  A table is consistent when, with I = roots[1],
+//   I^2 = -1,  roots[2k]^2 = roots[k],  roots[2k+1] = roots[2k] * I   (k >= 1),  every entry < q,
+// which is equivalent to roots[k] = psi^bitrev(k) for the primitive 2n-th root psi = roots[n/2]; precons (optional)
+// must be the Shoup companions floor(roots[k] * 2^32 / q).  Violations are counted in *bad.
+__global__ void __launch_bounds__(256) relayout_tables_kernel(TableSet t, const uint32_t *__restrict__ roots,
+                                                              const uint32_t *__restrict__ precons, bool inverse, uint32_t q,
+                                                              uint32_t n_inv, uint32_t logn, int le, unsigned *bad) {
+    const uint32_t n = 1u << logn;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t r = k ? roots[k] : 1u;
+    bool ok = r < q && r != 0;
+    if (ok && k >= 1) {
+        if (precons && precons[k] != shoup_pair(r, q).y) ok = false;
+        const uint32_t I = roots[1];
+        if (k == 1 && mulmod_dev(I, I, q) != q - 1) ok = false;
+        if (2 * k < n) {
+            const uint32_t e = roots[2 * k], o = roots[2 * k + 1];
+            if (e >= q || o >= q || mulmod_dev(e, e, q) != r || mulmod_dev(e, I % q, q) != o) ok = false;
         }
-        (inverse ? twc_inv : twc_fwd)[base + cpos] = cval;
-        if (inverse && j >= 1) twc_inv[base + cpos + 2] = natural;        // variant B: one 16-byte slot further
     }
+    if (!ok) { atomicAdd(bad, 1u); return; }
+    place_table_entry(t, k, r, inverse, q, n_inv, logn, le);
 }
 
 // ---------------------------------------------------------------------------------- synthetic data + checksum

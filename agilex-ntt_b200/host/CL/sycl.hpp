@@ -35,6 +35,10 @@ struct device_selector { virtual ~device_selector() = default; virtual int devic
 class queue {
     struct State {
         agx_ctx* ctx = nullptr;
+        // the round being assembled by the reference-named entry points (kernel/ntt.h): sizes seen so far, so that
+        // whichever of ntt_input_kernel / ntt_output_kernel comes second can check the output buffer against numFrames x N
+        size_t round_n = 0, round_out_words = 0;
+        long long round_out_frames = -1;
         ~State() { if (ctx) agx_destroy(ctx); }
     };
     std::shared_ptr<State> st_;
@@ -48,7 +52,20 @@ public:
     explicit queue(const device_selector& s) { init(s.device()); }
     queue(const device_selector& s, const async_handler&) { init(s.device()); }
     agx_ctx* native() const { return st_->ctx; }
+    // bookkeeping for ntt_shim.cpp; throws when the drain's buffer cannot hold numFrames x N words
+    void note_input(size_t n) { st_->round_n = n; check_round(); }
+    void note_output(size_t words, long long frames) { st_->round_out_words = words; st_->round_out_frames = frames; check_round(); }
+    void end_round() { st_->round_n = 0; st_->round_out_frames = -1; }
+private:
+    void check_round() {
+        if (st_->round_n && st_->round_out_frames >= 0) {
+            const bool bad = (size_t)st_->round_out_frames * st_->round_n > st_->round_out_words;
+            if (bad) { end_round(); throw exception(AGX_E_INVALID, "ntt_output_kernel: outData_buf is smaller than numFrames x N"); }
+        }
+    }
+public:
     void wait() {
+        end_round();
         const int rc = agx_wait(st_->ctx);
         if (rc) throw exception(rc, "sycl::queue::wait");
     }

@@ -12,8 +12,10 @@
  *   ntt_output_kernel(out, numFrames, q)                       agx_ref_output()     include/kernel/ntt.h:43-45,
  *                                                                                    src/kernel/ntt.cpp:610-640
  *   sycl::queue::wait()   (src/main.cpp:74)                    agx_wait()
- *   compile-time FPGA_NTT_SIZE / modulus buffer / twiddle      agx_parms + agx_create()   (the reference has no
- *   buffers (ntt.h:7-23, main.cpp:32-37)                       parameter struct)
+ *   compile-time FPGA_NTT_SIZE / modulus buffer                agx_parms + agx_create()   (the reference has no
+ *   (ntt.h:7-23, main.cpp:34)                                  parameter struct)
+ *   caller-filled twiddle / precon buffers                     agx_create_tables() (caller's psi), agx_set_tables()
+ *   (ntt.h:38-39, main.cpp:36-37,46-55, ntt.cpp:122-141)       (caller's tables in the reference's order)
  *
  * and the batched u32 entry points BASELINE.json's north_star adds (no reference counterpart):
  *   agx_ntt_fwd / agx_ntt_inv / agx_polymul on device pointers, *_host variants on host pointers.
@@ -24,14 +26,16 @@
  *     without a CUDA device agx_create() fails with the cudaError_t.
  *   - Transform definition (matches ntt.cpp): forward is negacyclic Cooley-Tukey, natural
  *     order in, BIT-REVERSED order out, outputs fully reduced to [0,q); inverse is Gentleman-Sande,
- *     bit-reversed in, natural out, n^-1 folded in.  psi = the minimal primitive 2n-th root of unity mod q.
+ *     bit-reversed in, natural out, n^-1 folded in.  psi = the minimal primitive 2n-th root of unity mod q unless the
+ *     caller supplies its own root (agx_create_tables) or its own tables (agx_set_tables).
  *   - Batched layout: uint32_t data[B][L][n] (B polynomials x L RNS limbs), row-major, in place.
  *     Inputs must be < 2q for the u32 entry points (uniform-mod-q data is < q).  Device pointers must be 16-byte
  *     aligned (anything from cudaMalloc is).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer calls only
  *     enqueue; completion follows normal stream semantics.  *_host calls return after the results are in
  *     host memory.
- *   - A context is bound to one device and is not thread-safe; use one context per host thread / GPU.
+ *   - A context is bound to one device and is not thread-safe; use one context per host thread / GPU.  Every call
+ *     makes the context's device current for its own duration and restores the caller's current device on return.
  */
 #ifndef AGXNTT_H
 #define AGXNTT_H
@@ -65,6 +69,24 @@ typedef struct {
 int agx_create(agx_ctx **out, const agx_parms *parms, int device);
 int agx_destroy(agx_ctx *ctx);
 
+/* The reference's contract is "the caller hands in the roots" (include/kernel/ntt.h:38-39; main.cpp:36-37,46-55 fill
+ * the buffers, ntt.cpp:122-141 receives them).  Two ways to do that on the u32 entry points:
+ *
+ * agx_create_tables: like agx_create, with the caller's primitive 2n-th root per limb, psi[nlimbs] (NULL = the
+ *   minimal root, i.e. agx_create).  AGX_E_INVALID unless psi[i]^n = -1 (mod q[i]).  The library derives the forward
+ *   and inverse tables from it on the device.
+ *
+ * agx_set_tables: replaces one limb's forward (inverse == 0) or inverse (inverse != 0) table by the caller's, given in
+ *   the reference's order (ntt.cpp:298-300: entry m + i is the twiddle of group i in the stage with m groups, i.e.
+ *   roots[k] = psi^bitrev(k) resp. psi^-bitrev(k); entry 0 is unused) as HOST arrays of n words.  precons[k] =
+ *   floor(roots[k] * 2^32 / q) -- the 32-bit counterpart of the reference's barrettTwiddleFactors buffer -- or NULL to
+ *   have them computed.  The table is checked on the device (roots[1]^2 = -1, roots[2k]^2 = roots[k], roots[2k+1] =
+ *   roots[2k] * roots[1], entries < q, precons exact) and re-laid-out for the kernels (the inverse one with n^-1
+ *   folded in); AGX_E_INVALID, with the previous table still in place, when it is not consistent.  A caller that
+ *   replaces the forward table replaces the inverse one too (the library does not derive one from the other). */
+int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi, int device);
+int agx_set_tables(agx_ctx *ctx, uint32_t limb, int inverse, const uint32_t *roots, const uint32_t *precons);
+
 /* Introspection (parity tests compare these with the oracle's tables). roots/precons in the reference's table
  * order, ntt.cpp:298-300: entry k = psi^bitrev(k) and floor(entry * 2^32 / q); inverse != 0 -> psi^-1. */
 int agx_get_psi(const agx_ctx *ctx, uint32_t limb, uint32_t *psi);
@@ -73,7 +95,10 @@ int agx_get_tables(const agx_ctx *ctx, uint32_t limb, int inverse, uint32_t *roo
 /* ---- batched u32 transforms on DEVICE pointers, in place, asynchronous on `stream` ---- */
 int agx_ntt_fwd(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
 int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
-/* c = a * b mod (X^n + 1, q_limb): forward(a), forward(b), pointwise, inverse in ONE launch. c may alias a or b. */
+/* c = a * b mod (X^n + 1, q_limb) = INTT(NTT(a) .* NTT(b)).  c may alias a and/or b, and a may equal b (squaring), at
+ * every size.  n = 1024 and 2048: forward(a), forward(b), pointwise product and inverse run in ONE launch (3 streams of
+ * HBM traffic); n = 4096: three launches (NTT(a); NTT(b) .* it; INTT -- 7 streams, no scratch memory); other sizes: the
+ * generic kernels with a stream-ordered scratch buffer. */
 int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
 
 /* ---- limb-wise element-wise arithmetic on [B][L][n] DEVICE data (the operations callers run around the transforms,
@@ -121,12 +146,27 @@ int agx_ref_fwd(agx_ctx *ctx, uint32_t compute_unit_id);
 int agx_ref_output(agx_ctx *ctx, uint64_t *out, int32_t numFrames);
 int agx_wait(agx_ctx *ctx);
 
+/* The same transform on DEVICE pointers, asynchronous on `stream` (what the three calls above run per chunk; exposes
+ * the kernels' rate without PCIe): frame b reads d_in[b*N .. b*N + N/2) and d_in2[b*N + N/2 .. (b+1)*N)
+ * (ntt.cpp:582-591) and writes d_out[b*N .. (b+1)*N) (ntt.cpp:626-633).  d_twiddles / d_precon_twiddles: N words each
+ * on the device.  d_out may be the same buffer as d_in AND d_in2 (in place) but must not overlap just one of them.
+ * Any 64-bit modulus: the arithmetic is the reference's, mod 2^64 (ntt.cpp:147-148, 331-369), so results are the
+ * reference's for every modulus it accepts; they are the NTT when q < 2^62 (lazy range [0,4q) inside 64 bits). */
+int agx_ref_fwd_dev(agx_ctx *ctx, uint32_t N, const uint64_t *d_in, const uint64_t *d_in2, uint64_t *d_out,
+                    uint64_t modulus, const uint64_t *d_twiddles, const uint64_t *d_precon_twiddles, uint32_t numFrames,
+                    void *stream);
+
 /* ---- diagnostics ---- */
 const char *agx_error_string(int code);
 /* kernels this library launched on ctx since creation (bench.py's gpu_launches claim) */
 int agx_launch_count(const agx_ctx *ctx, uint64_t *count);
 /* name of the kernel variant serving (n): "ntt2p<LOGN,LE>" or "generic" */
 int agx_variant(const agx_ctx *ctx, char *buf, size_t buflen);
+/* The measured integer roofline of this GPU: the butterfly's instruction stream alone (no memory operations), one CTA
+ * of `threads_per_sm` (128..1024, multiple of 128) threads per SM, timed in SM clocks.  kind 0: the u32 Harvey/Shoup
+ * butterfly of the batched kernels; kind 1: the u64 butterfly of the reference-shaped path (ntt.cpp:331-369).
+ * *per_clk_per_sm = butterflies retired per clock per SM; *sm_mhz (may be NULL) = the clock the run implied. */
+int agx_measure_butterfly_peak(agx_ctx *ctx, int kind, int threads_per_sm, double *per_clk_per_sm, double *sm_mhz);
 
 #ifdef __cplusplus
 }

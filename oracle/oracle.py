@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
         L.orc_tables_u32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u32p, u32p]
         L.orc_ref_fwd_u64.argtypes = [C.c_uint32, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint32, u64p]
         L.orc_fwd_u32_barrett.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p]
+        L.orc_powmod.restype = C.c_uint64
+        L.orc_powmod.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.orc_inv_u32_barrett.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p]
         L.orc_fwd_u32_shoup.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, u32p]
         L.orc_inv_u32_shoup.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p, u32p]
@@ -244,6 +246,34 @@ def ref_fwd_u64(in1, in2, modulus: int, roots, precons, num_frames: int = 1):
     out = np.empty(N * num_frames, dtype=np.uint64)
     lib().orc_ref_fwd_u64(N, _p64(in1), _p64(in2), modulus, _p64(roots), _p64(precons), num_frames, _p64(out))
     return out
+
+
+def fwd_u32_with_psi(x: np.ndarray, q: int, psi: int) -> np.ndarray:
+    """Forward transform of every row of x[...][n] with the caller's root psi (tables built from it the way ntt.cpp:298-300
+    consumes them), Harvey/Shoup-lazy butterflies (ntt.cpp:331-393 arithmetic at u32).  Returns a new array."""
+    n = x.shape[-1]
+    r, p = tables_u32(n, q, psi)
+    y = np.ascontiguousarray(x, dtype=np.uint32).copy()
+    for row in y.reshape(-1, n):
+        lib().orc_fwd_u32_shoup(n, q, _p32(r), _p32(p), row.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return y
+
+
+def inv_u32_with_psi(x: np.ndarray, q: int, psi: int) -> np.ndarray:
+    n = x.shape[-1]
+    r, p = tables_u32(n, q, psi, inverse=True)
+    y = np.ascontiguousarray(x, dtype=np.uint32).copy()
+    for row in y.reshape(-1, n):
+        lib().orc_inv_u32_shoup(n, q, _p32(r), _p32(p), row.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return y
+
+
+def primitive_roots_2n(n: int, q: int, count: int):
+    """The `count` smallest primitive 2n-th roots of unity mod q after the minimal one (odd powers of min_psi)."""
+    g = min_psi(n, q)
+    roots = sorted(pow(g, e, q) for e in range(1, 2 * n, 2))
+    assert roots[0] == g
+    return roots[1:1 + count]
 
 
 class Plan:

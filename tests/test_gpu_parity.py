@@ -76,6 +76,109 @@ def test_bad_parameters(A):
         A.Context(4096, [])                    # no limbs
 
 
+# ------------------------------------------------------------------------------- caller-supplied roots / tables
+
+# (q, psi) pairs SURVEY.md App. A recalls from SEAL-Embedded for n = 4096; each equals the minimal root of its prime
+SEAL_PSI_4096 = {134012929: 7470, 134111233: 3856, 134176769: 24149, 1053818881: 503422, 1054015489: 16768, 1054212097: 7305}
+
+
+@pytest.mark.parametrize("n", [64, 1024, 2048, 4096, 8192])
+def test_caller_psi_non_minimal(A, torch, n):
+    """agx_create_tables: the reference's contract is that the caller supplies the roots (include/kernel/ntt.h:38-39,
+    main.cpp:46-55); a scheme that fixes a non-minimal psi gets exactly that psi's transform (oracle with the same psi,
+    and the textbook definition at small n), forward and inverse, per limb."""
+    primes = Q if n <= 4096 else Q[:2]
+    psis = [O.primitive_roots_2n(n, q, 3)[l] for l, q in enumerate(primes)]      # a different non-minimal root per limb
+    c = A.Context(n, primes, psi=psis)
+    P = O.Plan(n, primes)
+    x = P.synthetic(9, seed=5)
+    d = to_dev(torch, x)
+    c.fwd(d)
+    y = to_np(d).reshape(x.shape)
+    for l, q in enumerate(primes):
+        assert c.psi(l) == psis[l] != O.min_psi(n, q)
+        want = O.fwd_u32_with_psi(x[:, l, :], q, psis[l])
+        assert (y[:, l, :] == want).all()
+        assert not (y[:, l, :] == P.fwd(x.copy())[:, l, :]).all()                  # and it is NOT the minimal-root transform
+        r, p = c.tables(l)
+        ro, po = O.tables_u32(n, q, psis[l])
+        assert (r == ro).all() and (p == po).all()
+        if n == 64:
+            assert (O.textbook_fwd(x[0, l], q, psis[l]) == y[0, l]).all()
+    c.inv(d)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    d2 = to_dev(torch, y)
+    c.inv(d2)
+    for l, q in enumerate(primes):
+        assert (to_np(d2).reshape(x.shape)[:, l, :] == O.inv_u32_with_psi(y[:, l, :], q, psis[l])).all()
+    if n <= 4096:                                                                  # the product does not depend on psi
+        a, b = P.synthetic(3, seed=1), P.synthetic(3, seed=2)
+        dc = torch.empty_like(to_dev(torch, a))
+        c.polymul(dc, to_dev(torch, a), to_dev(torch, b))
+        assert (to_np(dc).reshape(a.shape) == P.polymul(a, b)).all()
+    c.close()
+
+
+def test_caller_psi_seal_pairs_and_rejects(A, torch):
+    n = 4096
+    for q, psi in SEAL_PSI_4096.items():
+        c = A.Context(n, [q], psi=[psi])
+        assert c.psi(0) == psi == O.min_psi(n, q)
+        x = O.Plan(n, [q]).synthetic(2, seed=9)
+        d = to_dev(torch, x)
+        c.fwd(d)
+        assert (to_np(d).reshape(x.shape) == O.Plan(n, [q]).fwd(x.copy())).all()
+        c.close()
+    q = Q[0]
+    for bad in (0, 1, q - 1, q, 2, pow(O.min_psi(n, q), 2, q)):      # zero, order 1 / 2, out of range, not a 2n-th root, order n
+        with pytest.raises(A.AgxError):
+            A.Context(n, [q], psi=[bad])
+    with pytest.raises(ValueError):
+        A.Context(n, Q, psi=[1, 2])                                  # one psi per limb
+
+
+@pytest.mark.parametrize("n", [256, 1024, 2048, 4096])
+def test_caller_tables_in_reference_order(A, torch, n):
+    """agx_set_tables: roots / precons in the order ntt.cpp:298-300 consumes (entry m + i), as host arrays -- what
+    main.cpp:36-37,46-55 hands to ntt_input_kernel -- re-laid-out on the device for the kernels."""
+    primes = Q[:2]
+    c = A.Context(n, primes)
+    P = O.Plan(n, primes)
+    x = P.synthetic(6, seed=8)
+    psi1 = O.primitive_roots_2n(n, primes[1], 5)[4]
+    r, p = O.tables_u32(n, primes[1], psi1)
+    ri, pi = O.tables_u32(n, primes[1], psi1, inverse=True)
+    c.set_tables(1, r, p)                       # limb 1 forward: caller's roots and precons
+    c.set_tables(1, ri, None, inverse=True)     # limb 1 inverse: precons computed by the library
+    assert c.psi(1) == psi1 and c.psi(0) == O.min_psi(n, primes[0])
+    d = to_dev(torch, x)
+    c.fwd(d)
+    y = to_np(d).reshape(x.shape)
+    assert (y[:, 0, :] == P.fwd(x.copy())[:, 0, :]).all()                          # limb 0 untouched
+    assert (y[:, 1, :] == O.fwd_u32_with_psi(x[:, 1, :], primes[1], psi1)).all()
+    got = c.tables(1, inverse=True)
+    assert (got[0] == ri).all() and (got[1] == pi).all()
+    c.inv(d)
+    assert (to_np(d).reshape(x.shape) == x).all()
+    # inconsistent tables are refused and leave the previous ones in place
+    bad = r.copy(); bad[n // 2 + 3] ^= 1
+    with pytest.raises(A.AgxError):
+        c.set_tables(1, bad, None)
+    badp = p.copy(); badp[5] += 1
+    with pytest.raises(A.AgxError):
+        c.set_tables(1, r, badp)
+    with pytest.raises(A.AgxError):
+        c.set_tables(1, np.arange(n, dtype=np.uint32) + 2, None)                   # main.cpp:52's dummy "twiddles"
+    with pytest.raises(A.AgxError):
+        c.set_tables(0, r, p)                                                      # roots of another prime
+    with pytest.raises(A.AgxError):
+        c.set_tables(2, r, p)                                                      # limb out of range
+    d = to_dev(torch, x)
+    c.fwd(d)
+    assert (to_np(d).reshape(x.shape) == y).all()
+    c.close()
+
+
 # ------------------------------------------------------------------------------- forward / inverse vs oracle
 
 @pytest.mark.parametrize("n", [8, 32, 256, 1024, 2048, 4096, 8192, 32768])
@@ -415,6 +518,15 @@ def test_argument_errors(A, torch):
     assert L.agx_ntt_fwd(c._h, ctypes.c_void_p(buf.data_ptr() + 4), 1, None) == -1   # not 16-byte aligned
     assert L.agx_ntt_inv(c._h, ctypes.c_void_p(buf.data_ptr() + 8), 1, None) == -1
     assert L.agx_polymul(c._h, ctypes.c_void_p(16), None, None, 1, None) == -1
+    ok, off = ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(buf.data_ptr() + 4)
+    for op in range(4):                                        # element-wise operands are read as 16-byte vectors too
+        assert L.agx_elementwise(c._h, op, ok, off, ok, 1, None) == -1
+        assert L.agx_elementwise(c._h, op, ok, ok, off, 1, None) == -1
+        assert L.agx_elementwise(c._h, op, off, ok, ok, 1, None) == -1
+    assert L.agx_elementwise(c._h, 4, ok, ok, ok, 1, None) == -1
+    torch.cuda.synchronize()                                   # none of the refused calls may have poisoned the context
+    assert L.agx_elementwise(c._h, 0, ok, ok, ok, 1, None) == 0
+    torch.cuda.synchronize()
     assert L.agx_ntt_fwd_host(c._h, None, None, 3) == -1
     assert L.agx_ntt_fwd_host(c._h, None, None, 0) == 0
     assert L.agx_ntt_fwd(None, None, 0, None) == -1
@@ -603,3 +715,38 @@ def test_many_limbs_odd_batches(A, torch, n, L, B):
     out = np.empty_like(x)
     c.fwd_host(x.copy(), out)
     assert (out == P.fwd(x.copy())).all()
+
+
+@pytest.mark.parametrize("n", [256, 8192])
+def test_generic_sizes_polymul_aliasing(A, torch, n):
+    """every aliasing case agx_polymul documents also holds on the generic (any-n) path."""
+    primes = Q[:2]
+    c = ctx_for(A, n, primes)
+    P = O.Plan(n, primes)
+    a, b = P.synthetic(5, seed=21), P.synthetic(5, seed=22)
+    want, sq = P.polymul(a, b), P.polymul(a, a)
+    da, db = to_dev(torch, a), to_dev(torch, b)
+    out = torch.empty_like(da)
+    c.polymul(out, da, db)
+    assert (to_np(out).reshape(a.shape) == want).all()
+    t = da.clone(); c.polymul(t, t, db)                    # out == a
+    assert (to_np(t).reshape(a.shape) == want).all()
+    t = db.clone(); c.polymul(t, da, t)                    # out == b
+    assert (to_np(t).reshape(a.shape) == want).all()
+    c.polymul(out, da, da)                                 # a == b
+    assert (to_np(out).reshape(a.shape) == sq).all()
+    t = da.clone(); c.polymul(t, t, t)                     # all three
+    assert (to_np(t).reshape(a.shape) == sq).all()
+    assert (to_np(da).reshape(a.shape) == a).all() and (to_np(db).reshape(a.shape) == b).all()
+
+
+def test_measured_butterfly_peak_is_sane(A, torch):
+    """The integer roofline bench.py reports is measured on the GPU in front of it: IMAD.HI at half rate caps the u32
+    butterfly at 16 per clock per SM; the isolated stream must land under that and above 10."""
+    c = ctx_for(A, 4096, Q[:1])
+    v8, mhz = c.measure_butterfly_peak(0, 1024)
+    v4, _ = c.measure_butterfly_peak(0, 512)
+    assert 10.0 < v4 <= v8 * 1.02 and v8 <= 16.5, (v4, v8)
+    assert 500 < mhz < 3000
+    u64, _ = c.measure_butterfly_peak(1, 1024)
+    assert 0.5 < u64 < v8

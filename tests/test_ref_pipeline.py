@@ -214,3 +214,55 @@ def test_chunked_pipeline_many_frames(A, pinned, same):
         assert launches == 5 * 4
     assert (out == want).all()
     v_holder.clear()
+
+
+@pytest.mark.parametrize("N,bits", [(1024, 60), (8192, 50), (16384, 60), (32768, 50), (64, 60)])
+def test_device_pointer_entry_point(A, N, bits):
+    """agx_ref_fwd_dev: the same transform on device buffers (what the pipeline runs per chunk), in2 != in, separate
+    output and fully in place, against the restatement."""
+    import torch
+    q = O.U64_PRIMES[bits]
+    tw, pre = O.tables_u64(N, q)
+    frames = 5
+    x, x2 = O.synthetic_u64(N * frames, 3, 4 * q), O.synthetic_u64(N * frames, 4, 4 * q)
+    want = O.ref_fwd_u64(x, x2, q, tw, pre, frames)
+    dev = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    d_in, d_in2, d_tw, d_pre = dev(x), dev(x2), dev(tw), dev(pre)
+    d_out = torch.zeros_like(d_in)
+    p = A.RefPipeline()
+    p.fwd_dev(N, d_in, d_in2, d_out, q, d_tw, d_pre, frames)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().view(np.uint64) == want).all()
+    assert (d_in.cpu().numpy().view(np.uint64) == x).all()            # inputs untouched
+    same = O.ref_fwd_u64(x, x, q, tw, pre, frames)
+    p.fwd_dev(N, d_in, d_in, d_in, q, d_tw, d_pre, frames)            # in place
+    torch.cuda.synchronize()
+    assert (d_in.cpu().numpy().view(np.uint64) == same).all()
+    with pytest.raises(A.AgxError):                                   # output overlapping only one of the inputs
+        p.fwd_dev(N, d_in, d_in2, d_in, q, d_tw, d_pre, frames)
+    with pytest.raises(A.AgxError):
+        p.fwd_dev(N + 1, d_in, d_in2, d_out, q, d_tw, d_pre, frames)
+    p.close()
+
+
+def test_buffer_size_contract_is_checked(A):
+    """agx_ref_* take bare pointers, so the mirrors of ntt_input_kernel / ntt_output_kernel check that the
+    buffers describe numFrames x N (main.cpp:26-37) before anything is handed to the DMA engines."""
+    N, q = 64, O.SEAL_PRIMES_30[0]
+    tw, pre = O.tables_u64(N, q)
+    x = np.arange(N * 2, dtype=np.uint64)
+    mod = np.array([q], dtype=np.uint64)
+    p = A.RefPipeline()
+    with pytest.raises(ValueError):
+        p.ntt_input_kernel(x, x, mod, tw, pre, 3)                     # inputs hold 2 frames, 3 requested
+    with pytest.raises(ValueError):
+        p.ntt_input_kernel(x, x, mod, tw, pre[:-1], 2)
+    p.ntt_input_kernel(x, x, mod, tw, pre, 2)
+    p.fwd_ntt_kernel(0)
+    with pytest.raises(ValueError):
+        p.ntt_output_kernel(np.zeros(N * 2 - 1, dtype=np.uint64), 2)  # too small for 2 frames
+    out = np.zeros(N * 2, dtype=np.uint64)
+    p.ntt_output_kernel(out, 2)
+    p.wait()
+    assert (out == O.ref_fwd_u64(x, x, q, tw, pre, 2)).all()
+    p.close()
