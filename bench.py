@@ -4,14 +4,22 @@
 Metric (BASELINE.json): NTT+INTT pairs/sec at n=4096, one 30-bit prime, batch of 65,536 polynomials per GPU
 (configs[1]); a "step" is one forward launch + one inverse launch over the whole 1 GiB batch, in place, inputs
 resident in HBM.  Multi-GPU: one process per GPU (torchrun), the batch dimension is sharded with no data-path
-collective (weak scaling: 65,536 polynomials per GPU); the only collectives are the barrier and the max-over-ranks
-reduction of the timing.
+collective (weak scaling: 65,536 polynomials per GPU); the only collectives are the barrier, the max-over-ranks
+reduction of the timings and the gather of the parity checksums.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      # the CPU path timed on this box's host cores
 
-Prints ONE JSON line (rank 0).  Extra keys beyond the base contract: roofline, cpu_baseline, e2e, clocks,
-gpu_launches, kernels.
+Prints ONE JSON line (rank 0).  Beyond the base contract it carries, all measured in the same run but OUTSIDE the
+headline timed region:
+  roofline      dominant kernel vs the measured HBM peak AND vs the integer roofline measured on this GPU
+                (agx_measure_butterfly_peak: the butterfly instruction stream alone); `bound` names the lower one
+  sustained     >= 2 s of back-to-back steps with >= 100 NVML samples (clock, power, throttle reasons)
+  configs       BASELINE configs 3, 4 and the cfg-5 sizes (n = 1024, 2048), each with its own roofline
+  strong        cfg 5's fixed 2^31/n global batch split over the ranks (n = 1024, 2048, 4096)
+  parity_in_bench  FORWARD spectra of slices of every rank's shard against the oracle (global indices; shard sums
+                gathered on rank 0), the all-ranks forward checksum, and the K-round-trip checksum
+  cpu_baseline, e2e, clocks, gpu_launches, kernels
 """
 from __future__ import annotations
 
@@ -30,10 +38,12 @@ if ROOT not in sys.path:
 METRIC = "NTT+INTT/sec at n=4096, 30-bit q"
 UNIT = "pairs/s"
 N_DEFAULT = 4096
-PRIME = 1053818881                  # first 30-bit SEAL-Embedded prime
+PRIMES = (1053818881, 1054015489, 1054212097)   # SEAL-Embedded 30-bit primes
+PRIME = PRIMES[0]
 BATCH_PER_GPU = 65536               # configs[1]
 SEED = 1234                         # timing seed
 HBM_FALLBACK_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+PARITY_HEAD, PARITY_TAIL = 3072, 1024   # polynomials of every shard whose forward spectra are compared with the oracle
 
 
 def host_threads() -> int:
@@ -51,16 +61,26 @@ def env_int(name, default):
         return default
 
 
+def make_config(n: int, B: int, world: int, strong_total: int = 0) -> dict:
+    """The workload description -- identical for our arm and the reference arm."""
+    return {"workload": f"configs[1]: n={n} single 30-bit prime q={PRIME}, batch of {B} polynomials per GPU, "
+                        "forward NTT + inverse NTT over the batch, in place",
+            "n": n, "nlimbs": 1, "batch_per_gpu": B, "global_batch": strong_total or world * B,
+            "l2": f"inputs {B * n * 4 >> 20} MiB per GPU > 126 MB L2 (no flush needed)",
+            "parallelism": f"batch-sharded x{world}, no collective"}
+
+
 # ----------------------------------------------------------------------------------------------- clocks sampler
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock / power / throttle reasons of one GPU through NVML while a timed region runs."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, cuda_index: int):
+    def __init__(self, cuda_index: int, period_s: float = 0.002):
         self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
+        self.period = period_s
         self._stop = threading.Event()
         self._thr = None
         self._h = None
@@ -99,12 +119,13 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(self.period)
 
     def start(self):
         if self._h is not None:
             self._thr = threading.Thread(target=self._loop, daemon=True)
             self._thr.start()
+        return self
 
     def stop(self) -> dict:
         self._stop.set()
@@ -113,9 +134,10 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
                     "note": getattr(self, "error", "no samples")}
-        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "power_w_max": round(max(self.power), 1) if self.power else None}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_mhz_min": min(self.samples),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": round(max(self.power), 1) if self.power else None,
+                "power_w_median": round(statistics.median(self.power), 1) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -159,13 +181,14 @@ def reference_code_rate():
         return {"error": repr(e)}
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the path, on this box's host cores.
 
     The reference's own kernel (src/kernel/ntt.cpp) is built only for N in {32,1024,8192,16384,32768} (ntt.h:11-23,
     #error otherwise), forward only, and needs the oneAPI FPGA emulator; n=4096 forward+inverse therefore runs the
     oracle port (oracle/ntt_oracle.c, Harvey/Shoup lazy butterflies = the arithmetic of ntt.cpp:331-393 at u32),
-    OpenMP over polynomials on all host threads.  Each step is a bounded sample of the workload."""
+    OpenMP over polynomials on all host threads.  Same workload description as our arm; each STEP transforms a bounded
+    sample of the 65,536-polynomial batch (the throughput is per pair, so the sample size does not enter the ratio)."""
     if rank != 0:
         return
     from oracle import oracle as O
@@ -185,9 +208,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"n={args.n} single 30-bit prime q={PRIME}, forward+inverse NTT (configs[1]); "
-                               f"each step = bounded sample of {sample} polynomials of the 65,536-polynomial batch",
-                   "n": args.n, "nlimbs": 1, "batch_per_step": sample},
+        "config": make_config(args.n, args.batch, max(world, args.gpus)),
+        "sample_note": f"each step = bounded sample of {sample} of the {args.batch} polynomials (per-pair throughput)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} fwd+inv pairs per step x {args.steps} steps, Shoup-lazy C oracle, OpenMP",
                          "reference_code": reference_code_rate()},
@@ -208,14 +230,17 @@ def load_peak():
 
 
 def load_traffic(kernel_key: str):
+    """DRAM bytes per launch from the ncu --set full capture of this build (profiles/roofline_traffic.json names the
+    capture it was read from); None for kernels that were not captured."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        return d.get(kernel_key)
+        return d.get(kernel_key), d.get("_source")
     except Exception:
-        return None
+        return None, None
 
 
 def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import agilex_ntt_b200 as A
@@ -244,6 +269,36 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def gather_u64(v: int):
+        """Every rank's 64-bit value on every rank (as two 32-bit halves: no signed overflow anywhere)."""
+        t = torch.tensor([v & 0xFFFFFFFF, v >> 32], dtype=torch.int64, device=dev)
+        if world == 1:
+            return [v]
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [int(p[0]) | (int(p[1]) << 32) for p in parts]
+
+    stream = torch.cuda.current_stream()
+
+    def time_ms(fn, iters, warm=3):
+        """Mean ms per call of fn (CUDA events on the launching stream), max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        return max_over_ranks([e0.elapsed_time(e1) / iters])[0]
+
     n, L, B = args.n, 1, args.batch
     if args.total_batch:                        # strong scaling (SURVEY.md s.8(d) cfg 5): a fixed global batch split over the ranks
         if args.total_batch % world:
@@ -251,10 +306,46 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         B = args.total_batch // world
     ctx = A.Context(n, [PRIME], device=local_rank)
     data = torch.empty(B * L * n, dtype=torch.int32, device=dev)
-    ctx.fill_synthetic(data, seed=SEED, first_poly=rank * B)      # shard = slice of the global synthetic batch
-    chk0 = ctx.checksum(data, first_index=rank * B * L * n)
-    stream = torch.cuda.current_stream()
+    first_poly = rank * B
+    ctx.fill_synthetic(data, seed=SEED, first_poly=first_poly)    # shard = slice of the global synthetic batch
+    chk0 = ctx.checksum(data, first_index=first_poly * L * n)
 
+    # ---- parity BEFORE timing: the forward spectra themselves (a wrong-but-invertible transform would survive a round
+    # trip).  Head and tail slices of every rank's shard are checksummed with GLOBAL indices on the device, gathered,
+    # and compared on rank 0 with the oracle's transform of the same global slices; the whole-shard forward checksum is
+    # gathered too (reported, and compared with the oracle's whole batch when --full-parity).
+    ctx.fwd(data)
+    head, tail = min(PARITY_HEAD, B), min(PARITY_TAIL, B)
+    slice_sum = (ctx.checksum(data[: head * n], first_index=first_poly * n)
+                 + ctx.checksum(data[(B - tail) * n:], first_index=(first_poly + B - tail) * n)) % (1 << 64)
+    fwd_sum = ctx.checksum(data, first_index=first_poly * n)
+    slice_sums, fwd_sums = gather_u64(slice_sum), gather_u64(fwd_sum)
+    ctx.inv(data)
+    ok_roundtrip0 = ctx.checksum(data, first_index=first_poly * L * n) == chk0
+    parity = {"forward_vs_oracle": None}
+    if rank == 0:
+        from oracle import oracle as O
+        P = O.Plan(n, [PRIME])
+        thr = host_threads()
+        want = 0
+        for r in range(world):
+            for lo, cnt in ((r * B, head), (r * B + B - tail, tail)):
+                y = P.fwd(P.synthetic(cnt, seed=SEED, first_poly=lo), threads=thr)
+                want = (want + O.checksum_u32(y, first_index=lo * n)) % (1 << 64)
+        got = A.combine_checksums(slice_sums)
+        parity = {"forward_vs_oracle": "ok" if got == want else "FAILED",
+                  "what": f"forward spectra of the first {head} and last {tail} polynomials of each of the {world} shards "
+                          "(global indices), device checksums gathered over ranks == oracle's",
+                  "forward_checksum_all_ranks": f"{A.combine_checksums(fwd_sums):016x}"}
+        if args.full_parity:
+            want_all = 0
+            step = 8192
+            for lo in range(0, world * B, step):
+                y = P.fwd(P.synthetic(min(step, world * B - lo), seed=SEED, first_poly=lo), threads=thr)
+                want_all = (want_all + O.checksum_u32(y, first_index=lo * n)) % (1 << 64)
+            parity["forward_full_batch_vs_oracle"] = "ok" if want_all == A.combine_checksums(fwd_sums) else "FAILED"
+
+    # ---- headline: W warm-up steps, then exactly K timed steps
     for _ in range(args.warmup):
         ctx.fwd(data); ctx.inv(data)
     torch.cuda.synchronize()
@@ -280,13 +371,44 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     fwd_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
     inv_ms = [ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]
-    ok = ctx.checksum(data, first_index=rank * B * L * n) == chk0        # K round trips leave the batch unchanged
+    ok = ok_roundtrip0 and ctx.checksum(data, first_index=first_poly * L * n) == chk0   # K round trips leave the batch unchanged
+
+    # ---- sustained: >= 2 s of back-to-back steps with NVML sampled throughout (a 20 ms burst says nothing about clocks)
+    sustained = None
+    if args.sustain_s > 0:
+        per_step = total_ms / K
+        reps = max(K, int(args.sustain_s * 1e3 / per_step) + 1)
+        s_sampler = ClockSampler(local_rank, period_s=0.005)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        s_sampler.start()
+        e0.record(stream)
+        for _ in range(reps):
+            ctx.fwd(data); ctx.inv(data)
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        s_clocks = s_sampler.stop()
+        s_ms = max_over_ranks([e0.elapsed_time(e1)])[0]
+        sustained = {"seconds": s_ms * 1e-3, "steps": reps, "value": world * B * L * reps / (s_ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": s_ms / reps, "clocks": s_clocks}
+        ok = ok and ctx.checksum(data, first_index=first_poly * L * n) == chk0
+
+    # ---- the integer roofline of THIS GPU: the butterfly instruction stream alone, 8 and 4 warps per scheduler
+    bf_peak8, bf_mhz = ctx.measure_butterfly_peak(0, 1024)
+    bf_peak4, _ = ctx.measure_butterfly_peak(0, 512)
 
     # ---- end-to-end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
     e2e_steps = max(1, min(K, args.e2e_steps))
     host = torch.empty(B * L * n, dtype=torch.int32).pin_memory()
     host.copy_(data)
-    ctx.fwd_host(host); ctx.inv_host(host)                                # warm the pipeline (allocations)
+    ctx.fwd_host(host)                                                     # warm the pipeline (allocations) ...
+    ok_e2e_fwd = True
+    if rank == 0:                                                          # ... and check a forward result of the host path
+        from oracle import oracle as O
+        P = O.Plan(n, [PRIME])
+        yh = host[: 64 * n].numpy().view(np.uint32).reshape(64, 1, n)
+        ok_e2e_fwd = bool((yh == P.fwd(P.synthetic(64, seed=SEED, first_poly=0), threads=4)).all())
+    ctx.inv_host(host)
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -294,57 +416,153 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         ctx.inv_host(host)
     torch.cuda.synchronize(); barrier()
     e2e_s = time.perf_counter() - t0
-    ok_e2e = bool((host[: 64 * n].to(dev) == data[: 64 * n]).all())
+    ok_e2e = ok_e2e_fwd and bool((host[: 64 * n].to(dev) == data[: 64 * n]).all()) and \
+        bool((host[-64 * n:].to(dev) == data[-64 * n:]).all())
+    del host
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(fwd_ms), statistics.mean(inv_ms),
-                      0.0 if (ok and ok_e2e) else 1.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, fwd_avg, inv_avg, bad = [float(v) for v in t.tolist()]
+    total_ms, e2e_ms, fwd_avg, inv_avg, bad = max_over_ranks(
+        [total_ms, e2e_s * 1e3, statistics.mean(fwd_ms), statistics.mean(inv_ms), 0.0 if (ok and ok_e2e) else 1.0])
+
+    peak, peak_src = load_peak()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def roofline_of(kernel, nn, transforms, ms, bytes_per_unit, mhz, traffic_key=None, bf_per_transform=None):
+        """One kernel (or fused op) against both rooflines: algorithmic bytes / measured HBM peak, and butterflies per
+        clock per SM / the measured isolated-stream rate.  `bound` = whichever roofline allows fewer units per second."""
+        logn = nn.bit_length() - 1
+        byts = float(bytes_per_unit) * transforms
+        achieved = byts / (ms * 1e-3) / 1e9
+        bf = (nn // 2) * logn if bf_per_transform is None else bf_per_transform
+        bf_rate = transforms * bf / (ms * 1e-3) / (sms * mhz * 1e6)
+        hbm_units_s = peak * 1e9 / bytes_per_unit
+        int_units_s = bf_peak8 * sms * mhz * 1e6 / bf
+        traffic, tsrc = load_traffic(traffic_key) if traffic_key else (None, None)
+        return {"bound": "hbm" if hbm_units_s <= int_units_s else "integer", "kernel": kernel, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": byts, "launch_ms": ms,
+                "frac_of_8TBs": achieved / 8000.0,
+                "integer": {"achieved": bf_rate, "peak": bf_peak8, "unit": "butterflies/clk/SM", "frac": bf_rate / bf_peak8,
+                            "peak_4_warps_per_scheduler": bf_peak4, "peak_issue_limit_imad_hi_half_rate": 16.0,
+                            "sm_mhz": mhz, "peak_source": "agx_measure_butterfly_peak on this GPU in this run "
+                                                          f"(isolated butterfly stream, implied clock {bf_mhz:.0f} MHz)"},
+                "roofline_units_per_s": {"hbm": hbm_units_s, "integer": int_units_s}}
+
+    # ---- every other BASELINE config, device-resident, own buffers, same event method (outside the headline region)
+    configs = {}
+    if not args.no_extras:
+        mhz_x = (sustained or {}).get("clocks", {}).get("sm_mhz") or clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+        del data
+        torch.cuda.empty_cache()
+
+        def ntt_case(nn, LL, BB, key, what):
+            c = A.Context(nn, PRIMES[:LL], device=local_rank)
+            d = torch.empty(BB * LL * nn, dtype=torch.int32, device=dev)
+            c.fill_synthetic(d, seed=SEED, first_poly=rank * BB)
+            s0 = c.checksum(d, first_index=rank * BB * LL * nn)
+            tf = time_ms(lambda: c.fwd(d), args.extra_iters)
+            ti = time_ms(lambda: c.inv(d), args.extra_iters)
+            c.fwd(d); c.inv(d)
+            good = c.checksum(d, first_index=rank * BB * LL * nn) == s0
+            T = BB * LL
+            configs[key] = {"workload": what, "n": nn, "nlimbs": LL, "batch_per_gpu": BB,
+                            "value": world * T / ((tf + ti) * 1e-3), "unit": "pairs/s",
+                            "fwd_ms": tf, "inv_ms": ti, "variant": c.variant(), "round_trip": "ok" if good else "FAILED",
+                            "roofline": roofline_of(("ntt_inv" if ti >= tf else "ntt_fwd") + f"<{c.variant()}>", nn, T,
+                                                    max(tf, ti), 2 * nn * 4, mhz_x)}
+            del d
+            c.close()
+            return good
+
+        good = ntt_case(4096, 3, 32768, "cfg3", "configs[2]: n=4096, 3-limb RNS (SEAL-Embedded 30-bit primes), batch of 32,768")
+        # cfg 4: negacyclic polynomial multiply n=2048, batch of 131,072: 3 n 4 B of algorithmic traffic per product
+        nn, BB = 2048, 131072
+        c = A.Context(nn, [PRIME], device=local_rank)
+        a, b = (torch.empty(BB * nn, dtype=torch.int32, device=dev) for _ in range(2))
+        out = torch.empty_like(a)
+        c.fill_synthetic(a, seed=1, first_poly=rank * BB)
+        c.fill_synthetic(b, seed=2, first_poly=rank * BB)
+        l0 = c.launch_count()
+        c.polymul(out, a, b)
+        per_call = c.launch_count() - l0
+        tp = time_ms(lambda: c.polymul(out, a, b), args.extra_iters)
+        pm_ok = True
+        if rank == 0:                    # exact schoolbook on a few products, NTT-path oracle on a slice
+            from oracle import oracle as O
+            P = O.Plan(nn, [PRIME])
+            xa, xb = P.synthetic(256, seed=1), P.synthetic(256, seed=2)
+            got = out[: 256 * nn].cpu().numpy().view(np.uint32).reshape(256, 1, nn)
+            pm_ok = bool((got == P.polymul(xa, xb, threads=host_threads())).all())
+            for i in (0, 255):
+                pm_ok = pm_ok and bool((O.polymul_schoolbook(xa[i, 0], xb[i, 0], PRIME) == got[i, 0]).all())
+        logn = 11
+        configs["cfg4"] = {"workload": "configs[3]: negacyclic polynomial multiply n=2048 (NTT, pointwise modmul, INTT), batch of 131,072",
+                           "n": nn, "nlimbs": 1, "batch_per_gpu": BB, "value": world * BB / (tp * 1e-3), "unit": "products/s",
+                           "ms": tp, "launches_per_call": per_call, "vs_oracle_and_schoolbook": "ok" if pm_ok else "FAILED",
+                           "roofline": roofline_of(f"polymul<n={nn}>, {per_call} launch(es)", nn, BB, tp, 3 * nn * 4, mhz_x,
+                                                   bf_per_transform=3 * (nn // 2) * logn)}
+        good = good and pm_ok
+        del a, b, out
+        c.close()
+        for nn in (1024, 2048):
+            good = ntt_case(nn, 1, (1 << 28) // nn, f"cfg5_n{nn}",
+                            f"configs[4] size n={nn}: single prime, 2^28/n = {(1 << 28) // nn} polynomials (1 GiB) per GPU") and good
+        # strong scaling: cfg 5's fixed global batch of 2^31/n polynomials (8 GiB) split contiguously over the ranks
+        strong = {}
+        if not args.no_strong:
+            for nn in (1024, 2048, 4096):
+                total = (1 << 31) // nn
+                BB = total // world
+                c = A.Context(nn, [PRIME], device=local_rank)
+                d = torch.empty(BB * nn, dtype=torch.int32, device=dev)
+                c.fill_synthetic(d, seed=SEED, first_poly=rank * BB)
+                s0 = c.checksum(d, first_index=rank * BB * nn)
+                tf = time_ms(lambda: c.fwd(d), 5, warm=2)
+                ti = time_ms(lambda: c.inv(d), 5, warm=2)
+                c.fwd(d); c.inv(d)
+                rt = c.checksum(d, first_index=rank * BB * nn) == s0
+                good = good and rt
+                strong[f"n{nn}"] = {"global_batch": total, "batch_per_gpu": BB, "fwd_ms": tf, "inv_ms": ti,
+                                    "value": total / ((tf + ti) * 1e-3), "unit": "pairs/s", "scaling": "strong",
+                                    "round_trip": "ok" if rt else "FAILED"}
+                del d
+                c.close()
+        bad = max_over_ranks([bad, 0.0 if good else 1.0])[0]
+    else:
+        strong = {}
 
     if rank == 0:
-        peak, peak_src = load_peak()
-        bytes_per_launch = 2.0 * n * 4 * B * L                      # read once + write once
         dom, dom_ms = ("ntt_fwd_kernel", fwd_avg) if fwd_avg >= inv_avg else ("ntt_inv_kernel", inv_avg)
-        achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9
         variant = ctx.variant()
-        # integer-multiply roofline: IMAD.HI issues at 32 lanes/clk/SM, so one butterfly holds the
-        # multiply pipe for 8 of its 64 lane-clocks -> 16 butterflies/clk/SM (agx_microbench measured 14.9)
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
         mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
-        logn = n.bit_length() - 1
-        bf_rate = B * L * (n // 2) * logn / (dom_ms * 1e-3) / (sms * mhz * 1e6)
+        bytes_per_launch = 2.0 * n * 4 * B * L                      # read once + write once (SURVEY.md s.8(d))
+        roof = roofline_of(f"{dom}<{variant}>", n, B * L, dom_ms, 2 * n * 4, mhz, traffic_key=dom)
+        failed = bad != 0.0 or parity.get("forward_vs_oracle") != "ok" or parity.get("forward_full_batch_vs_oracle") == "FAILED"
+        parity["round_trips_and_e2e"] = "ok" if bad == 0.0 else "FAILED"
         line = {
             "metric": METRIC, "value": world * B * L * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
             "scaling": "strong" if args.total_batch else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: n={n} single 30-bit prime q={PRIME}, batch of {B} polynomials per GPU, "
-                                   "forward launch + inverse launch in place",
-                       "n": n, "nlimbs": L, "batch_per_gpu": B, "global_batch": world * B,
-                       "l2": f"inputs {B * L * n * 4 >> 20} MiB per GPU > 126 MB L2 (no flush needed)",
-                       "kernel_variant": variant, "parallelism": f"batch-sharded x{world}, no collective"},
-            "roofline": {"bound": "hbm", "kernel": f"{dom}<{variant[6:-1]}>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(dom),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "launch_ms": dom_ms, "frac_of_8TBs": achieved / 8000.0,
-                         "imad_butterflies_per_clk_per_sm": bf_rate, "imad_peak_butterflies_per_clk_per_sm": 16.0,
-                         "imad_frac": bf_rate / 16.0,
-                         "binding": "integer multiply pipe (IMAD.HI at half rate; 189 M transforms/s at 1965 MHz "
-                                    "vs 200 M/s from measured HBM)"},
+            "config": make_config(n, B, world, args.total_batch),
+            "kernel_variant": variant,
+            "roofline": roof,
             "kernels": {"ntt_fwd_ms": fwd_avg, "ntt_inv_ms": inv_avg,
                         "fwd_transforms_per_s": B * L / (fwd_avg * 1e-3), "inv_transforms_per_s": B * L / (inv_avg * 1e-3),
                         "fwd_GBps": bytes_per_launch / (fwd_avg * 1e-3) / 1e9,
-                        "inv_GBps": bytes_per_launch / (inv_avg * 1e-3) / 1e9},
+                        "inv_GBps": bytes_per_launch / (inv_avg * 1e-3) / 1e9,
+                        "fwd_frac_of_measured_hbm": bytes_per_launch / (fwd_avg * 1e-3) / 1e9 / peak,
+                        "inv_frac_of_measured_hbm": bytes_per_launch / (inv_avg * 1e-3) / 1e9 / peak},
+            "sustained": sustained,
             "e2e": {"value": world * B * L * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * B * L * n * 4, "d2h_bytes_per_step": 2 * B * L * n * 4,
                     "steps": e2e_steps, "api": "agx_ntt_fwd_host + agx_ntt_inv_host on pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "parity_in_bench": "round trip + e2e spot check " + ("ok" if bad == 0.0 else "FAILED"),
+            "configs": configs,
+            "strong": strong,
+            "parity_in_bench": parity,
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu:
-            from oracle import oracle as O
             thr = host_threads()
             sample = args.cpu_sample
             reps = 8                      # 262,144 pairs ~ 12 CPU-seconds of the Shoup-lazy port
@@ -358,8 +576,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                     "barrett_value": vb, "single_core_value": v1,
                                     "reference_code": reference_code_rate()}
         print(json.dumps(line), flush=True)
-        if bad != 0.0:
-            raise SystemExit("bench.py: parity check inside the bench FAILED")
+        if failed:
+            raise SystemExit("bench.py: parity check inside the bench FAILED: " + json.dumps(parity))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -377,8 +595,13 @@ def main():
     ap.add_argument("--total-batch", type=int, default=0,
                     help="strong scaling: fixed global batch split contiguously over the GPUs (cfg 5 uses 2^31/n)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--sustain-s", type=float, default=2.2, help="length of the sustained block (0 = skip)")
+    ap.add_argument("--extra-iters", type=int, default=20, help="timed launches per extra config")
     ap.add_argument("--cpu-sample", type=int, default=32768, help="polynomials in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip BASELINE configs 3-5 and the strong-scaling block")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--full-parity", action="store_true", help="also compare the whole forward batch with the oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -390,7 +613,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 
