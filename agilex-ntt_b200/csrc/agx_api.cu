@@ -13,6 +13,15 @@
 
 #include "agx_ntt_kernels.cuh"
 #include "agx_diag.cuh"
+// Build-time option, OFF in the shipped library: the radix-16 three-pass kernels for n = 4096 (16 coefficients per thread,
+// 40 warps per SM).  Bit-exact, measured 6-9 % slower than the two-pass kernels (profiles/r02_experiments.md), kept out of
+// the product tree; a variant library with them is built by `make -C experiments r16` and selected with AGX_KERNEL=r16.
+#ifndef AGX_WITH_R16
+#define AGX_WITH_R16 0
+#endif
+#if AGX_WITH_R16
+#include "agx_ntt_r16.cuh"
+#endif
 #include "agx_tables.h"
 
 using namespace agx;
@@ -69,12 +78,17 @@ struct agx_ctx {
     uint2 *d_twc_fwd = nullptr, *d_twc_inv = nullptr;      // column-pass tables (two-pass kernels only)
     LimbConst *d_lc = nullptr;
     LimbConst lc0 = {};                                    // limb 0, passed by value in the kernel parameters
+    bool r16 = false;                                      // AGX_WITH_R16 builds only
+#if AGX_WITH_R16
+    uint2 *d_tw16_fwd = nullptr, *d_tw16_inv = nullptr, *d_u16_fwd = nullptr, *d_u16_inv = nullptr;
+    uint2 u16_fwd0[kR16UInv] = {}, u16_inv0[kR16UInv] = {};   // limb 0's uniform twiddles, passed by value
+#endif
     unsigned long long *d_sum = nullptr;
     uint64_t launches = 0;
     // TMA tensor maps over result buffers (forward kernels store through cp.async.bulk.tensor): the encoder entry
     // point of the driver, and the maps of the most recently used (pointer, polynomial count) pairs
     void *encode_tiled = nullptr;
-    struct MapSlot { const void *ptr = nullptr; size_t T = 0; CUtensorMap map; };
+    struct MapSlot { const void *ptr = nullptr; size_t T = 0; int kind = 0; CUtensorMap map; };
     MapSlot maps[8];
     unsigned map_next = 0;
     HostPipe pipe;
@@ -110,6 +124,8 @@ public:
 #define AGX_ON_DEVICE(c)                    \
     DeviceGuard guard__((c)->device);       \
     if (guard__.error()) return guard__.error()
+
+int refresh_r16(agx_ctx *c);
 
 // Per-limb scalars on the host (psi search, inverses, Barrett constants); the n-entry tables themselves are
 // computed on the device by gen_tables_kernel.
@@ -164,7 +180,17 @@ int build_tables(agx_ctx *c, const uint32_t *psi_in) {
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
     cudaFree(d_lg);
-    return (int)e;
+    if (e != cudaSuccess) return (int)e;
+#if AGX_WITH_R16
+    if (c->r16) {
+        CK(cudaMalloc(&c->d_tw16_fwd, entries * sizeof(uint2)));
+        CK(cudaMalloc(&c->d_tw16_inv, entries * sizeof(uint2)));
+        CK(cudaMalloc(&c->d_u16_fwd, (size_t)L * kR16UFwd * sizeof(uint2)));
+        CK(cudaMalloc(&c->d_u16_inv, (size_t)L * kR16UInv * sizeof(uint2)));
+        return refresh_r16(c);
+    }
+#endif
+    return AGX_OK;
 }
 
 KParams kparams(const agx_ctx *c) {
@@ -186,7 +212,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 const CUtensorMap *result_map(agx_ctx *c, void *ptr, size_t T, uint32_t E, uint32_t TPP) {
     if (!AGX_TMA_STORE || !c->encode_tiled || (reinterpret_cast<uintptr_t>(ptr) & 15) || T * TPP > 0x7fffffffull) return nullptr;   // box coordinates are signed 32-bit
     for (auto &m : c->maps)
-        if (m.ptr == ptr && m.T == T) return &m.map;
+        if (m.ptr == ptr && m.T == T && m.kind == 0) return &m.map;
     agx_ctx::MapSlot &m = c->maps[c->map_next++ % 8];
     const cuuint64_t gdim[3] = {32, E / 32, (cuuint64_t)T * TPP};
     const cuuint64_t gstr[2] = {128, (cuuint64_t)E * 4};
@@ -195,9 +221,66 @@ const CUtensorMap *result_map(agx_ctx *c, void *ptr, size_t T, uint32_t E, uint3
         &m.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { m.ptr = nullptr; return nullptr; }
-    m.ptr = ptr; m.T = T;
+    m.ptr = ptr; m.T = T; m.kind = 0;
     return &m.map;
 }
+
+#if AGX_WITH_R16
+// Tensor map of the radix-16 kernels: the batch as rows of 32 words, {32, T * n/32}, box {32, n/32} = one polynomial
+// as a dense 128-byte-swizzled tile; serves the forward kernel's store and the inverse kernel's load.
+const CUtensorMap *tile_map(agx_ctx *c, const void *ptr, size_t T, uint32_t n) {
+    const uint32_t rows = n / 32;
+    if (!c->encode_tiled || (reinterpret_cast<uintptr_t>(ptr) & 15) || T * rows > 0x7fffffffull || rows > 256) return nullptr;
+    for (auto &m : c->maps)
+        if (m.ptr == ptr && m.T == T && m.kind == 1) return &m.map;
+    agx_ctx::MapSlot &m = c->maps[c->map_next++ % 8];
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)T * rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {32, rows}, estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+        &m.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { m.ptr = nullptr; return nullptr; }
+    m.ptr = ptr; m.T = T; m.kind = 1;
+    return &m.map;
+}
+
+// (Re)derives what the radix-16 kernels read from the context's natural-order tables: the kernel-order copies and
+// the uniform twiddles of the first forward / last inverse pass (entries k < 16, the inverse ones with n^-1 folded in).
+int refresh_r16(agx_ctx *c) {
+    if (!c->r16) return AGX_OK;
+    const uint32_t n = c->n, L = c->L, entries = L * n;
+    r16_relayout_kernel<<<(entries + 255) / 256, 256>>>(c->d_tw16_fwd, c->d_nat_fwd, c->logn, entries);
+    r16_relayout_kernel<<<(entries + 255) / 256, 256>>>(c->d_tw16_inv, c->d_nat_inv, c->logn, entries);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    std::vector<uint2> uf((size_t)L * kR16UFwd), ui((size_t)L * kR16UInv), nat(16);
+    for (uint32_t l = 0; l < L; l++) {
+        const uint64_t q = c->q[l], s = c->n_inv[l];
+        auto pair = [&](uint64_t w) { return make_uint2((uint32_t)w, (uint32_t)((w << 32) / q)); };
+        CK(cudaMemcpy(nat.data(), c->d_nat_fwd + (size_t)l * n, 16 * sizeof(uint2), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 16; k++) uf[(size_t)l * kR16UFwd + k] = nat[k];
+        CK(cudaMemcpy(nat.data(), c->d_nat_inv + (size_t)l * n, 16 * sizeof(uint2), cudaMemcpyDeviceToHost));
+        uint2 *u = ui.data() + (size_t)l * kR16UInv;
+        for (int g = 0; g < 8; g++) u[g] = pair(mulmod_u64(nat[8 + g].x, s, q));
+        for (int g = 0; g < 4; g++) { u[8 + g] = pair(mulmod_u64(nat[4 + g].x, s, q)); u[12 + g] = nat[4 + g]; }
+        for (int g = 0; g < 2; g++) { u[16 + g] = pair(mulmod_u64(nat[2 + g].x, s, q)); u[18 + g] = nat[2 + g]; }
+        u[20] = nat[1]; u[21] = pair(s); u[22] = pair(mulmod_u64(nat[1].x, s, q)); u[23] = make_uint2(0, 0);
+    }
+    CK(cudaMemcpy(c->d_u16_fwd, uf.data(), uf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_u16_inv, ui.data(), ui.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    for (int k = 0; k < kR16UInv; k++) { c->u16_fwd0[k] = k < kR16UFwd ? uf[k] : make_uint2(0, 0); c->u16_inv0[k] = ui[k]; }
+    return AGX_OK;
+}
+
+R16Params r16params(const agx_ctx *c, bool inverse) {
+    R16Params p{c->d_tw16_fwd, c->d_tw16_inv, c->d_u16_fwd, c->d_u16_inv, c->d_lc, c->L, c->lc0, {}};
+    for (int k = 0; k < kR16UInv; k++) p.u[k] = inverse ? c->u16_inv0[k] : c->u16_fwd0[k];
+    return p;
+}
+#else
+int refresh_r16(agx_ctx *) { return AGX_OK; }
+#endif
 
 template <int LOGN, int LE, bool CL>
 int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
@@ -281,10 +364,50 @@ int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const ui
     return (int)cudaGetLastError();
 }
 
+#if AGX_WITH_R16
+// n = 4096 through the radix-16 three-pass kernels; false when a tensor map cannot be encoded for these buffers (the
+// caller then takes the two-pass kernels, which serve every case)
+template <bool CL>
+bool launch_r16(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s, int *rc) {
+    using G = R16<12>;
+    const CUtensorMap *tm = tile_map(c, out, T, G::N);
+    if (!tm) return false;
+    const dim3 grid((unsigned)T), block(G::TPP);
+    const uint32_t Tu = (uint32_t)T;
+    if (op == OP_FWD) {
+        r16_fwd_kernel<12, false, CL><<<grid, block, 0, s>>>(out, out, nullptr, r16params(c, false), Tu, *tm);
+        c->launches++;
+    } else if (op == OP_INV) {
+        r16_inv_kernel<12, CL><<<grid, block, 0, s>>>(out, r16params(c, true), Tu, *tm);
+        c->launches++;
+    } else {
+        // three launches, no scratch buffer: out = NTT(a); out = NTT(b) .* out; out = INTT(out)
+        if (out == b && out != a) { const uint32_t *t = a; a = b; b = t; }     // the product commutes
+        r16_fwd_kernel<12, false, CL><<<grid, block, 0, s>>>(out, a, nullptr, r16params(c, false), Tu, *tm);
+        if (a == b) {
+            const size_t total = T * G::N;
+            pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, out, c->d_lc, c->L, 12, total);
+        } else {
+            r16_fwd_kernel<12, true, CL><<<grid, block, 0, s>>>(out, b, out, r16params(c, false), Tu, *tm);
+        }
+        r16_inv_kernel<12, CL><<<grid, block, 0, s>>>(out, r16params(c, true), Tu, *tm);
+        c->launches += 3;
+    }
+    *rc = (int)cudaGetLastError();
+    return true;
+}
+#endif
+
 int launch(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t B, cudaStream_t s) {
     const size_t T = B * c->L;
     if (T == 0) return AGX_OK;
     if (T > 0x7fffffffull) return AGX_E_INVALID;
+#if AGX_WITH_R16
+    if (c->r16) {
+        int rc = 0;
+        if (c->L == 1 ? launch_r16<true>(c, op, out, a, b, T, s, &rc) : launch_r16<false>(c, op, out, a, b, T, s, &rc)) return rc;
+    }
+#endif
     switch (c->le ? c->logn : 0) {
         // single-limb batches run the instantiation whose modulus constants are constant-bank operands
         case 12: return c->L == 1 ? launch_fast<12, 6, true>(c, op, out, a, b, T, s) : launch_fast<12, 6, false>(c, op, out, a, b, T, s);
@@ -463,7 +586,25 @@ int ref_launch(agx_ctx *c, uint32_t logn, const uint64_t *d_in, const uint64_t *
                const uint64_t *d_pre, uint64_t modulus, size_t frames, cudaStream_t st) {
     const uint32_t N = 1u << logn;
     const size_t frame_bytes = (size_t)N * 8;
-    static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knob: one-CTA-per-frame radix-2 kernel
+    static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knobs: one-CTA-per-frame radix-2 kernel,
+    static const bool passes_only = getenv("AGX_REF_PASSES") != nullptr;   // ... the multi-launch pass kernels
+    // One launch, frame resident in shared memory (two CTAs per frame at N = 32768, which is unsafe in place: the CTA of
+    // one half would overwrite what the other has not read yet).
+    const bool in_place = d_out == d_in || d_out == d_in2;
+    if (logn >= 10 && !naive && !passes_only && !(logn == 15 && in_place)) {
+        const uint32_t split = logn == 15 ? 1u : 0u, lg = logn - split;
+        const size_t smem = ((size_t)17 << (lg - 4)) * 8;
+        const unsigned grid = (unsigned)(frames << split);
+        switch (lg) {
+            case 14:
+            case 13: ref_u64_frame_kernel<512><<<grid, 512, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 12: ref_u64_frame_kernel<256><<<grid, 256, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 11: ref_u64_frame_kernel<128><<<grid, 128, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            default: ref_u64_frame_kernel<64><<<grid, 64, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+        }
+        c->launches++;
+        return (int)cudaGetLastError();
+    }
     if (logn >= 10 && !naive) {
         // register-radix passes over the L2-resident chunk: logN - 4 strided stages in groups of <= 4, then the
         // last 4 stages on contiguous 16-coefficient runs (with the final reduction)
@@ -639,6 +780,9 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
         cudaError_t e = cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        const int frame_smem = 17 * 1024 * 8;                          // N = 16384 image: 136 KB
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem / 4);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bitrev_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e != cudaSuccess) { delete c; return (int)e; }
     }
@@ -648,6 +792,12 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
         c->has_parms = true;
         c->n = parms->n; c->logn = parms->logn; c->L = parms->nlimbs;
         c->le = select_le(c->logn);
+#if AGX_WITH_R16
+        {   // n = 4096: radix-16 three-pass kernels (they need the TMA tensor-map encoder), selected with AGX_KERNEL=r16
+            const char *k = getenv("AGX_KERNEL");
+            c->r16 = c->logn == 12 && c->encode_tiled && k && strcmp(k, "r16") == 0;
+        }
+#endif
         c->q.assign(parms->q, parms->q + parms->nlimbs);
         c->psi.resize(c->L);
         c->n_inv.resize(c->L);
@@ -677,6 +827,9 @@ int agx_destroy(agx_ctx *c) {
         cudaFree(c->d_tw_fwd); cudaFree(c->d_tw_inv); cudaFree(c->d_nat_fwd); cudaFree(c->d_nat_inv);
         cudaFree(c->d_twc_fwd); cudaFree(c->d_twc_inv);
         cudaFree(c->d_lc); cudaFree(c->d_sum);
+#if AGX_WITH_R16
+        cudaFree(c->d_tw16_fwd); cudaFree(c->d_tw16_inv); cudaFree(c->d_u16_fwd); cudaFree(c->d_u16_inv);
+#endif
     }
     delete c;
     return AGX_OK;
@@ -737,7 +890,8 @@ int agx_set_tables(agx_ctx *c, uint32_t limb, int inverse, const uint32_t *roots
     }
     cudaFree(d_in); cudaFree(d_new); cudaFree(d_bad);
     if (e != cudaSuccess) return (int)e;
-    return bad ? AGX_E_INVALID : AGX_OK;
+    if (bad) return AGX_E_INVALID;
+    return refresh_r16(c);
 }
 
 int agx_ntt_fwd(agx_ctx *c, uint32_t *d, size_t B, void *stream) {
@@ -975,6 +1129,7 @@ int agx_launch_count(const agx_ctx *c, uint64_t *count) {
 int agx_variant(const agx_ctx *c, char *buf, size_t buflen) {
     if (!c || !buf || !buflen) return AGX_E_INVALID;
     if (!c->has_parms) snprintf(buf, buflen, "ref_u64");
+    else if (c->r16) snprintf(buf, buflen, "ntt_r16<%u>", c->logn);
     else if (c->le) snprintf(buf, buflen, "ntt2p<%u,%d>", c->logn, c->le);
     else snprintf(buf, buflen, "generic");
     return AGX_OK;

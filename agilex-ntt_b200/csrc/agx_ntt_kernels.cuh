@@ -869,6 +869,141 @@ __global__ void __launch_bounds__(128) ref_u64_last_pass_kernel(uint64_t *data, 
     }
 }
 
+// ---------------------------------------------------------------- reference-shaped u64 forward: one launch per round
+// The whole frame lives in ONE CTA's shared memory (N <= 16384: 128 KB + padding; a B200 SM offers 227 KB), so a frame is
+// read from HBM once and written once instead of making logN/4 round trips: loader, compute unit and drain of the
+// reference (ntt.cpp:508-607, 86-506, 610-640) in one kernel.  N = 32768 (256 KB) takes two CTAs per frame: stage 0
+// pairs x[i] with x[i + N/2] (ntt.cpp:292-300 with m = 1), after which the halves are independent 16384-point
+// sub-transforms; each CTA reads both halves, keeps its own output of stage 0 and carries on alone (costs one extra
+// stage of arithmetic in 15, no exchange between CTAs).
+// 512 threads per SM at <= 128 registers (the 64-bit butterfly with its twiddle pairs in flight does not fit 64, measured:
+// 570 bytes of spills), so the 1024 "virtual threads" of a 16384-point frame are two rounds of a 512-thread CTA.
+// Every "virtual thread" keeps 16 coefficients in registers per pass (index bits [lo, lo+4) vary inside the thread) and
+// runs up to 4 stages on them; passes go from the top index bits down to bit 4 -- the last of those may be partial --
+// and a final pass works on bits 3..0, i.e. on 16 consecutive coefficients.  Image in shared memory: a row of 16
+// coefficients every 17 words of 8 bytes (A(idx) = idx + idx/16), which makes every pass's 64-bit accesses
+// conflict-free: lanes walk along a row when lo >= 4, and down the rows at a 136-byte pitch when lo = 0.
+// Arithmetic: ref_bfly_u64 (ntt.cpp:331-369 mod 2^64, any tables), final reduction ntt.cpp:377-393.
+template <int JFIRST>
+__device__ __forceinline__ void ref_pass16_u64(uint64_t (&x)[16], const uint64_t *__restrict__ roots,
+                                               const uint64_t *__restrict__ precons, uint32_t s_first, uint32_t t_hi, uint64_t q,
+                                               uint64_t twice) {
+    // local stage j (JFIRST..3) is global stage s_first + (j - JFIRST); pairs x[g*2h + i], x[g*2h + i + h], h = 8 >> j;
+    // twiddle index m + i of ntt.cpp:298-300 = 2^s + (t_hi << j) + g
+#pragma unroll
+    for (int j = JFIRST; j < 4; j++) {
+        const int h = 8 >> j;
+        const uint32_t tbase = (1u << (s_first + j - JFIRST)) + (t_hi << j);
+#pragma unroll
+        for (int g = 0; g < (1 << j); g++) {
+            const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
+#pragma unroll
+            for (int i = 0; i < h; i++) ref_bfly_u64(x[g * 2 * h + i], x[g * 2 * h + i + h], W, Wp, q, twice);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint64_t *in, const uint64_t *in2,   // may alias each other and out
+                                                              uint64_t *out, const uint64_t *__restrict__ roots,
+                                                              const uint64_t *__restrict__ precons, uint64_t q, uint32_t logn,
+                                                              uint32_t split) {
+    // split = 0: one CTA per frame, logn <= 14.  split = 1: two CTAs per frame (logn = 15), CTA parity = which half.
+    extern __shared__ uint64_t img[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t frame = split ? blockIdx.x >> 1 : blockIdx.x, half_id = split ? blockIdx.x & 1u : 0u;
+    const uint32_t lg = logn - split;                              // log2 of the coefficients this CTA owns
+    const uint32_t M = 1u << lg, vthreads = M >> 4;
+    const uint64_t twice = q << 1;
+    const size_t fbase = (size_t)frame << logn;
+    const uint64_t *lo_src = in + fbase, *hi_src = in2 + fbase;    // low / high half of the frame (ntt.cpp:587-589)
+    uint64_t x[16];
+
+    // ---- pass 0: stages (split ..) on index bits [lg-4, lg), coefficients straight from global memory
+    {
+        const uint32_t lo = lg - 4;
+        for (uint32_t vt = tid; vt < vthreads; vt += NT) {
+            if (split) {
+                // stage 0 of the 32768-point frame, this CTA keeping only its half (ntt.cpp:331-369 with roots[1])
+                const uint64_t W = __ldg(roots + 1), Wp = __ldg(precons + 1);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t i = (k << lo) + vt;
+                    uint64_t a = lo_src[i], b = hi_src[M + i];
+                    ref_bfly_u64(a, b, W, Wp, q, twice);
+                    x[k] = half_id ? b : a;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t i = (k << lo) + vt;
+                    x[k] = (k < 8 ? lo_src : hi_src)[i];
+                }
+            }
+            // this CTA's sub-transform: stage s of it is global stage s + split, group offset half_id << s
+            // (roots index = 2^(s+split) + (half_id << s) + local group)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int h = 8 >> j;
+                const uint32_t tbase = (1u << (j + split)) + (half_id << j);
+#pragma unroll
+                for (int g = 0; g < (1 << j); g++) {
+                    const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
+#pragma unroll
+                    for (int i = 0; i < h; i++) ref_bfly_u64(x[g * 2 * h + i], x[g * 2 * h + i + h], W, Wp, q, twice);
+                }
+            }
+            uint64_t *s = img + vt + (vt >> 4);
+            const uint32_t stride = (1u << lo) + (1u << (lo - 4));
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[k * stride] = x[k];
+        }
+    }
+    __syncthreads();
+    // ---- middle passes: index bits from lg-5 down to 4, four at a time (the last one may cover fewer)
+    uint32_t s_done = 4;                                           // stages of the sub-transform finished so far
+    for (int rem = (int)lg - 8; rem > 0; rem -= 4) {
+        const uint32_t lo = rem >= 4 ? (uint32_t)rem : 4u;
+        const uint32_t jfirst = rem >= 4 ? 0u : (uint32_t)(4 - rem);
+        const uint32_t stride = (1u << lo) + (1u << (lo - 4));
+        for (uint32_t vt = tid; vt < vthreads; vt += NT) {
+            const uint32_t t_lo = vt & ((1u << lo) - 1), t_hi = vt >> lo;
+            const uint32_t idx0 = (t_hi << (lo + 4)) + t_lo;
+            uint64_t *s = img + idx0 + (idx0 >> 4);
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = s[k * stride];
+            // twiddle index: 2^(s+split) + ((half_id << s) + group) with group = (t_hi << j) + g at local stage j
+            const uint32_t sg = s_done + split;                    // global stage of the first active local stage
+            const uint32_t th = t_hi + (half_id << (s_done - jfirst));   // the CTA's half as the top bit of the group index
+            if (jfirst == 0) ref_pass16_u64<0>(x, roots, precons, sg, th, q, twice);
+            else if (jfirst == 1) ref_pass16_u64<1>(x, roots, precons, sg, th, q, twice);
+            else if (jfirst == 2) ref_pass16_u64<2>(x, roots, precons, sg, th, q, twice);
+            else ref_pass16_u64<3>(x, roots, precons, sg, th, q, twice);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[k * stride] = x[k];
+        }
+        s_done += 4 - jfirst;
+        __syncthreads();
+    }
+    // ---- final pass: bits 3..0 (16 consecutive coefficients), reduction to [0,q) (ntt.cpp:377-393)
+    for (uint32_t vt = tid; vt < vthreads; vt += NT) {
+        uint64_t *s = img + vt * 17;
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = s[k];
+        ref_pass16_u64<0>(x, roots, precons, s_done + split, vt + (half_id << s_done), q, twice);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint64_t v = x[k];
+            if (v >= twice) v -= twice;
+            if (v >= q) v -= q;
+            s[k] = v;
+        }
+    }
+    __syncthreads();
+    uint64_t *dst = out + fbase + (size_t)half_id * M;
+    for (uint32_t i = tid; i < M; i += NT) dst[i] = img[i + (i >> 4)];
+}
+
 // ------------------------------------------------------------------------------------- twiddle tables on device
 // The step before the path: the reference fills its root / precon buffers on the host (main.cpp:46-55) and the loader
 // broadcasts them (ntt.cpp:544-571).  Here one thread per (limb, direction, k) computes
