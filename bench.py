@@ -286,17 +286,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     stream = torch.cuda.current_stream()
 
+    last_mhz = [None]
+
     def time_ms(fn, iters, warm=3):
-        """Mean ms per call of fn (CUDA events on the launching stream), max over ranks."""
+        """Mean ms per call of fn (CUDA events on the launching stream), max over ranks; the SM clock NVML saw while the
+        timed launches ran is left in last_mhz[0]."""
         for _ in range(warm):
             fn()
         barrier(); torch.cuda.synchronize()
+        smp = ClockSampler(local_rank, period_s=0.001).start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(iters):
             fn()
         e1.record(stream)
-        torch.cuda.synchronize(); barrier()
+        torch.cuda.synchronize()
+        last_mhz[0] = smp.stop().get("sm_mhz")
+        barrier()
         return max_over_ranks([e0.elapsed_time(e1) / iters])[0]
 
     n, L, B = args.n, 1, args.batch
@@ -461,6 +467,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             s0 = c.checksum(d, first_index=rank * BB * LL * nn)
             tf = time_ms(lambda: c.fwd(d), args.extra_iters)
             ti = time_ms(lambda: c.inv(d), args.extra_iters)
+            mhz_c = last_mhz[0] or mhz_x
             c.fwd(d); c.inv(d)
             good = c.checksum(d, first_index=rank * BB * LL * nn) == s0
             T = BB * LL
@@ -468,7 +475,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                             "value": world * T / ((tf + ti) * 1e-3), "unit": "pairs/s",
                             "fwd_ms": tf, "inv_ms": ti, "variant": c.variant(), "round_trip": "ok" if good else "FAILED",
                             "roofline": roofline_of(("ntt_inv" if ti >= tf else "ntt_fwd") + f"<{c.variant()}>", nn, T,
-                                                    max(tf, ti), 2 * nn * 4, mhz_x)}
+                                                    max(tf, ti), 2 * nn * 4, mhz_c)}
             del d
             c.close()
             return good
@@ -485,6 +492,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         c.polymul(out, a, b)
         per_call = c.launch_count() - l0
         tp = time_ms(lambda: c.polymul(out, a, b), args.extra_iters)
+        mhz_p = last_mhz[0] or mhz_x
         pm_ok = True
         if rank == 0:                    # exact schoolbook on a few products, NTT-path oracle on a slice
             from oracle import oracle as O
@@ -498,7 +506,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         configs["cfg4"] = {"workload": "configs[3]: negacyclic polynomial multiply n=2048 (NTT, pointwise modmul, INTT), batch of 131,072",
                            "n": nn, "nlimbs": 1, "batch_per_gpu": BB, "value": world * BB / (tp * 1e-3), "unit": "products/s",
                            "ms": tp, "launches_per_call": per_call, "vs_oracle_and_schoolbook": "ok" if pm_ok else "FAILED",
-                           "roofline": roofline_of(f"polymul<n={nn}>, {per_call} launch(es)", nn, BB, tp, 3 * nn * 4, mhz_x,
+                           "roofline": roofline_of(f"polymul<n={nn}>, {per_call} launch(es)", nn, BB, tp, 3 * nn * 4, mhz_p,
                                                    bf_per_transform=3 * (nn // 2) * logn)}
         good = good and pm_ok
         del a, b, out
@@ -526,6 +534,55 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                     "round_trip": "ok" if rt else "FAILED"}
                 del d
                 c.close()
+        # the reference-shaped u64 path on device-resident frames (agx_ref_fwd_dev): N = 16384 (the reference's default,
+        # main.cpp:9,27), a 60-bit NTT prime, 256 MiB of frames per GPU; fraction of the 2 N 8 B HBM roofline and of the
+        # u64 integer roofline measured on this GPU (the ntt.cpp:331-369 butterfly stream alone)
+        u64 = None
+        try:
+            N64, q64 = 16384, 1152921504606584833
+            psi = next(c for c in (pow(g, (q64 - 1) // (2 * N64), q64) for g in range(2, 200)) if pow(c, N64, q64) == q64 - 1)
+            pw = [1] * N64
+            for i in range(1, N64):
+                pw[i] = pw[i - 1] * psi % q64
+            lg = N64.bit_length() - 1
+            roots = [pw[int(format(k, f"0{lg}b")[::-1], 2)] for k in range(N64)]
+            tw = np.array(roots, dtype=np.uint64)
+            pre = np.array([(w << 64) // q64 for w in roots], dtype=np.uint64)
+            frames = (256 << 20) // (N64 * 8)
+            d_tw = torch.from_numpy(tw.view(np.int64)).to(dev)
+            d_pre = torch.from_numpy(pre.view(np.int64)).to(dev)
+            gen = torch.Generator(device=dev); gen.manual_seed(SEED + rank)
+            d_in = torch.randint(0, 4 * q64, (frames * N64,), dtype=torch.int64, device=dev, generator=gen)   # lazy [0,4q)
+            d_out = torch.empty_like(d_in)
+            rp = A.RefPipeline(device=local_rank)
+            rp.fwd_dev(N64, d_in, d_in, d_out, q64, d_tw, d_pre, frames)
+            torch.cuda.synchronize()
+            ok64 = True
+            if rank == 0:
+                from oracle import oracle as O
+                xin = d_in[: 2 * N64].cpu().numpy().view(np.uint64)
+                ok64 = bool((d_out[: 2 * N64].cpu().numpy().view(np.uint64) == O.ref_fwd_u64(xin, xin, q64, tw, pre, 2)).all())
+            t64 = time_ms(lambda: rp.fwd_dev(N64, d_in, d_in, d_out, q64, d_tw, d_pre, frames), args.extra_iters)
+            mhz_u = last_mhz[0] or mhz_x
+            peak64, _ = ctx.measure_butterfly_peak(1, 1024)
+            fps = world * frames / (t64 * 1e-3)
+            bf64 = (N64 // 2) * lg
+            rate = frames * bf64 / (t64 * 1e-3) / (sms * mhz_u * 1e6)
+            hbm_fps, int_fps = peak * 1e9 / (2 * N64 * 8), peak64 * sms * mhz_u * 1e6 / bf64
+            u64 = {"workload": f"reference-shaped u64 forward NTT (agx_ref_fwd_dev), N={N64}, 60-bit prime, {frames} frames per GPU, "
+                               "lazy [0,4q) inputs, device resident",
+                   "value": fps, "unit": "frames/s", "ms": t64, "vs_restatement": "ok" if ok64 else "FAILED",
+                   "roofline": {"bound": "hbm" if hbm_fps <= int_fps else "integer", "achieved": frames * 2 * N64 * 8 / (t64 * 1e-3) / 1e9,
+                                "peak": peak, "unit": "GB/s", "frac": frames * 2 * N64 * 8 / (t64 * 1e-3) / 1e9 / peak, "traffic": None,
+                                "integer": {"achieved": rate, "peak": peak64, "unit": "u64 butterflies/clk/SM", "frac": rate / peak64,
+                                            "sm_mhz": mhz_u},
+                                "roofline_units_per_s": {"hbm": hbm_fps, "integer": int_fps}}}
+            good = good and ok64
+            del d_in, d_out
+            rp.close()
+        except Exception as e:       # a context number: never let it take the headline line down
+            u64 = {"error": repr(e)}
+        configs["u64_n16384"] = u64
         bad = max_over_ranks([bad, 0.0 if good else 1.0])[0]
     else:
         strong = {}

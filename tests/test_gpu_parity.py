@@ -575,24 +575,6 @@ def test_elementwise_rns_ops(A, torch):
     assert (to_np(d[0]).reshape(a.shape) == want).all()
 
 
-def test_two_devices_one_process(A, torch):
-    """One context per GPU inside one process (the C ABI's multi-GPU model when the caller is not multi-process)."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    n = 8192                                   # generic kernel: 32 KB of dynamic shared memory, > 48 KB path at 16384
-    for nn in (n, 16384):
-        P = O.Plan(nn, Q[:1])
-        x = P.synthetic(6, seed=2)
-        want = P.fwd(x.copy())
-        for dev in (0, 1):
-            c = A.Context(nn, Q[:1], device=dev)
-            with torch.cuda.device(dev):
-                d = torch.from_numpy(x.view(np.int32)).cuda(dev)
-                c.fwd(d)
-                assert (to_np(d).reshape(x.shape) == want).all()
-            c.close()
-
-
 def test_five_limbs_and_27bit_primes(A, torch):
     """Limb counts that divide nothing, and smaller (27-bit) primes: the limb index is poly % L inside the kernels and
     the Barrett constants depend on the bit length of q."""

@@ -97,3 +97,19 @@ def test_device_is_restored_by_every_entry_point(A, torch):
     assert (_np(d).reshape(x.shape) == x).all()
     c.close()
     assert torch.cuda.current_device() == 0
+
+
+def test_generic_sizes_on_every_visible_gpu(A, torch):
+    """One context per GPU inside one process (the C ABI's multi-GPU model when the caller is not multi-process), sizes
+    served by the generic kernel: 32 KB of dynamic shared memory at n = 8192, the > 48 KB opt-in path at 16384 -- function
+    attributes are per-device state."""
+    for nn in (8192, 16384):
+        P = O.Plan(nn, Q[:1])
+        x = P.synthetic(6, seed=2)
+        want = P.fwd(x.copy())
+        for dev in range(torch.cuda.device_count()):
+            c = A.Context(nn, Q[:1], device=dev)
+            d = torch.from_numpy(x.view(np.int32)).cuda(dev)
+            c.fwd(d, stream=torch.cuda.current_stream(dev))
+            assert (_np(d).reshape(x.shape) == want).all()
+            c.close()
