@@ -96,9 +96,10 @@ int agx_get_tables(const agx_ctx *ctx, uint32_t limb, int inverse, uint32_t *roo
 int agx_ntt_fwd(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
 int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
 /* c = a * b mod (X^n + 1, q_limb) = INTT(NTT(a) .* NTT(b)).  c may alias a and/or b, and a may equal b (squaring), at
- * every size.  n = 1024 and 2048: forward(a), forward(b), pointwise product and inverse run in ONE launch (3 streams of
- * HBM traffic); n = 4096: three launches (NTT(a); NTT(b) .* it; INTT -- 7 streams, no scratch memory); other sizes: the
- * generic kernels with a stream-ordered scratch buffer. */
+ * every size.  n = 1024: forward(a), forward(b), pointwise product and inverse run in ONE launch (3 streams of HBM
+ * traffic); n = 2048 and 4096: three launches (c = NTT(a); c = NTT(b) .* c; c = INTT(c) -- 7 streams, no scratch
+ * memory; the product is bound by the integer-multiply pipe, not by that traffic: DESIGN.md s.4); other sizes: the
+ * generic kernels, with a stream-ordered scratch buffer unless a == b. */
 int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
 
 /* ---- limb-wise element-wise arithmetic on [B][L][n] DEVICE data (the operations callers run around the transforms,
@@ -135,7 +136,9 @@ int agx_checksum(agx_ctx *ctx, const uint32_t *d_data, size_t count, size_t firs
 
 /* ---- reference-shaped u64 forward pipeline (host pointers; mirrors main.cpp:60-74) ----
  * N in {2^2 .. 2^15} (the reference builds 32, 1024, 8192, 16384, 32768: ntt.h:11-20).  Arithmetic is the
- * reference's u64 Harvey butterfly including wrap-around mod 2^64 for tables that are not Shoup pairs.
+ * reference's u64 Harvey butterfly including wrap-around mod 2^64 for tables that are not Shoup pairs -- and for
+ * moduli of 62 bits and more, whose lazy range [0,4q) no longer fits 64 bits (the reference wraps identically; parity
+ * is pinned on 50-, 60-, 62- and 63-bit primes against the reference's own code).
  * The three calls only record/enqueue, in any order (the reference's three kernels run concurrently); the work
  * runs once all three were made; agx_wait() blocks until `out` is filled (= q.wait()).  `in`, `in2` hold
  * numFrames*N words (frame b: low half from in[b*N..], high half from in2[b*N + N/2..], ntt.cpp:582-591);
