@@ -1068,7 +1068,7 @@ int agx_ref_fwd_dev(agx_ctx *c, uint32_t N, const uint64_t *d_in, const uint64_t
 }
 
 int agx_measure_butterfly_peak(agx_ctx *c, int kind, int threads_per_sm, double *per_clk_per_sm, double *sm_mhz) {
-    if (!c || !per_clk_per_sm || kind < 0 || kind > 1) return AGX_E_INVALID;
+    if (!c || !per_clk_per_sm || kind < 0 || kind > 6) return AGX_E_INVALID;
     if (threads_per_sm < 128 || threads_per_sm > 1024 || threads_per_sm % 128) return AGX_E_INVALID;
     AGX_ON_DEVICE(c);
     uint32_t *d_out = nullptr;
@@ -1087,8 +1087,18 @@ int agx_measure_butterfly_peak(agx_ctx *c, int kind, int threads_per_sm, double 
     if (e == cudaSuccess) {
         for (int rep = 0; rep < 2; rep++) {                // first launch warms the clocks and the instruction cache
             if (rep == 1) cudaEventRecord(e0, 0);
-            if (kind == 0) diag_bfly_kernel<0><<<sms, threads_per_sm>>>(d_out, d_cyc, 12345u, lc, q64);
-            else diag_bfly_kernel<1><<<sms, threads_per_sm>>>(d_out, d_cyc, 12345u, lc, q64);
+            const uint2 wc = make_uint2(12345u | 1u, 12345u * 3u + 5u);
+#define AGX_DIAG(K) diag_bfly_kernel<K><<<sms, threads_per_sm>>>(d_out, d_cyc, 12345u, lc, q64, wc)
+            switch (kind) {
+                case 0: AGX_DIAG(0); break;
+                case 1: AGX_DIAG(1); break;
+                case 2: AGX_DIAG(2); break;
+                case 3: AGX_DIAG(3); break;
+                case 4: AGX_DIAG(4); break;
+                case 5: AGX_DIAG(5); break;
+                default: AGX_DIAG(6); break;
+            }
+#undef AGX_DIAG
             c->launches++;
         }
         cudaEventRecord(e1, 0);

@@ -167,7 +167,9 @@ int agx_launch_count(const agx_ctx *ctx, uint64_t *count);
 int agx_variant(const agx_ctx *ctx, char *buf, size_t buflen);
 /* The measured integer roofline of this GPU: the butterfly's instruction stream alone (no memory operations), one CTA
  * of `threads_per_sm` (128..1024, multiple of 128) threads per SM, timed in SM clocks.  kind 0: the u32 Harvey/Shoup
- * butterfly of the batched kernels; kind 1: the u64 butterfly of the reference-shaped path (ntt.cpp:331-369).
+ * butterfly of the batched kernels; kind 1: the u64 butterfly of the reference-shaped path (ntt.cpp:331-369); kind 2 / 3:
+ * kind 0 with one / two extra non-multiply instructions per butterfly (the issue-slot load of a real kernel); kinds 4-6:
+ * further variants of the stream used by profiles/diag_issue_pressure.py (see csrc/agx_diag.cuh).
  * *per_clk_per_sm = butterflies retired per clock per SM; *sm_mhz (may be NULL) = the clock the run implied. */
 int agx_measure_butterfly_peak(agx_ctx *ctx, int kind, int threads_per_sm, double *per_clk_per_sm, double *sm_mhz);
 
