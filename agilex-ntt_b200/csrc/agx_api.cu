@@ -786,6 +786,13 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bitrev_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e != cudaSuccess) { delete c; return (int)e; }
     }
+    if (const char *e = getenv("AGX_CARVEOUT")) {      // A/B knob: shared-memory carve-out (percent) of the n = 4096 kernels
+        const int pct = atoi(e);
+        cudaFuncSetAttribute(ntt_fwd_loop_kernel<12, 6, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(ntt_fwd_loop_kernel<12, 6, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(ntt_inv_loop_kernel<12, 6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(ntt_inv_loop_kernel<12, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     if (parms) {
         if (!parms->q || parms->nlimbs == 0 || parms->nlimbs > 64 || parms->logn < 3 || parms->logn > 15 ||
             parms->n != (1u << parms->logn)) { delete c; return AGX_E_INVALID; }

@@ -301,6 +301,13 @@ __device__ __forceinline__ void tma_store_poly(const uint4 *sm, const CUtensorMa
 #ifndef AGX_MINB
 #define AGX_MINB(LOGN, LE) ((1 << (LE)) >= 64 ? (AGX_THREADS_E64 >> ((LOGN) - (LE))) : (768 >> ((LOGN) - (LE))))
 #endif
+// A/B knob: an explicit register cap for the 64-coefficient kernels instead of a minimum CTA count
+// (-DAGX_MAXNREG_E64=112 -> 9 CTAs of 64 threads per SM)
+#ifdef AGX_MAXNREG_E64
+#define AGX_KERNEL_BOUNDS(LOGN, LE) __launch_bounds__(1 << ((LOGN) - (LE))) __maxnreg__((1 << (LE)) >= 64 ? AGX_MAXNREG_E64 : 80)
+#else
+#define AGX_KERNEL_BOUNDS(LOGN, LE) __launch_bounds__(1 << ((LOGN) - (LE)), AGX_MINB(LOGN, LE))
+#endif
 
 // ------------------------------------------------------------------------------ looped two-pass kernels
 // The fully unrolled passes above are ~47 KB of SASS per kernel; with 16 warps per SM each at a different point
@@ -436,7 +443,7 @@ __device__ __forceinline__ void inv_last_stage(uint32_t (&x)[1 << LE], const uin
 // TMA: results leave through tma_store_rows (dst is then described by `tmap`); otherwise through the padded staging
 // image and coalesced 16-byte stores.
 template <int LOGN, int LE, bool MUL, bool CL, bool TMA = false>
-__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+__global__ void AGX_KERNEL_BOUNDS(LOGN, LE)
 ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KParams p, uint32_t T,
                     const __grid_constant__ CUtensorMap tmap) {
     using G = Geo<LOGN, LE>;
@@ -499,7 +506,7 @@ ntt_fwd_loop_kernel(uint32_t *dst, const uint32_t *src, const uint32_t *mul, KPa
 }
 
 template <int LOGN, int LE, bool CL>
-__global__ void __launch_bounds__(1 << (LOGN - LE), AGX_MINB(LOGN, LE))
+__global__ void AGX_KERNEL_BOUNDS(LOGN, LE)
 ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     using G = Geo<LOGN, LE>;
     __shared__ uint4 sm[G::SMEM_CHUNKS];
