@@ -589,18 +589,22 @@ int ref_launch(agx_ctx *c, uint32_t logn, const uint64_t *d_in, const uint64_t *
     static const bool naive = getenv("AGX_REF_NAIVE") != nullptr;   // A/B knobs: one-CTA-per-frame radix-2 kernel,
     static const bool passes_only = getenv("AGX_REF_PASSES") != nullptr;   // ... the multi-launch pass kernels
     // One launch, frame resident in shared memory (two CTAs per frame at N = 32768, which is unsafe in place: the CTA of
-    // one half would overwrite what the other has not read yet).
+    // one half would overwrite what the other has not read yet).  Splitting N = 16384 the same way -- two independent
+    // 8192-point halves per SM instead of one 136 KB CTA -- measured +5 % on a 1 GiB batch and -5 % on a 16 MiB chunk:
+    // not done.
     const bool in_place = d_out == d_in || d_out == d_in2;
     if (logn >= 10 && !naive && !passes_only && !(logn == 15 && in_place)) {
         const uint32_t split = logn == 15 ? 1u : 0u, lg = logn - split;
         const size_t smem = ((size_t)17 << (lg - 4)) * 8;
         const unsigned grid = (unsigned)(frames << split);
+        // N/32 threads per CTA, two virtual threads each (512 at N = 16384, the largest frame an SM holds): below that
+        // several independent CTAs share an SM and cover each other's barriers and load phases
         switch (lg) {
-            case 14:
-            case 13: ref_u64_frame_kernel<512><<<grid, 512, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
-            case 12: ref_u64_frame_kernel<256><<<grid, 256, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
-            case 11: ref_u64_frame_kernel<128><<<grid, 128, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
-            default: ref_u64_frame_kernel<64><<<grid, 64, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 14: ref_u64_frame_kernel<512><<<grid, 512, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 13: ref_u64_frame_kernel<256><<<grid, 256, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 12: ref_u64_frame_kernel<128><<<grid, 128, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            case 11: ref_u64_frame_kernel<64><<<grid, 64, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
+            default: ref_u64_frame_kernel<32><<<grid, 32, smem, st>>>(d_in, d_in2, d_out, d_tw, d_pre, modulus, logn, split); break;
         }
         c->launches++;
         return (int)cudaGetLastError();
@@ -782,7 +786,7 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         const int frame_smem = 17 * 1024 * 8;                          // N = 16384 image: 136 KB
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem / 4);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem / 2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(bitrev_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e != cudaSuccess) { delete c; return (int)e; }
     }
