@@ -224,6 +224,46 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
     for (int i = 0; i < G::N / 4 / G::TPP; i++) s[i * (G::TPP / G::CPR) * G::PITCH4] = v[i];
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Inverse-kernel input.  Shipped (AGX_INV_INPUT = 3): cp.async (LDGSTS.128: L2 -> shared memory without passing registers
+// or allocating in L1), and each warp stages exactly the rows its own threads will read (warp w: rows 32w .. 32w+31,
+// 8 KB contiguous in global memory), so a __syncwarp replaces the CTA barrier: inverse 0.4983 -> 0.4943 ms in one call
+// (profiles/r02_experiments.md).  A/B values: 0 = LDG.128 -> registers -> STS.128 (global_to_smem above) + CTA barrier
+// (round 1), 1 = cp.async + CTA barrier (0.4979-0.4983), 2 = warp-local rows with LDG/STS (0.5011).
+#ifndef AGX_INV_INPUT
+#define AGX_INV_INPUT 3
+#endif
+template <int LOGN, int LE>
+__device__ __forceinline__ void inv_stage_input(uint4 *sm, const uint32_t *g, uint32_t tid) {
+    using G = Geo<LOGN, LE>;
+    constexpr int NCH = G::N / 4 / G::TPP;               // 16-byte chunks per thread
+    constexpr bool WARP_LOCAL = (AGX_INV_INPUT & 2) != 0 && G::TPP > 32;
+    constexpr bool ASYNC = (AGX_INV_INPUT & 1) != 0;
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
+    uint4 v[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+        // chunk index c of the polynomial: row c / CPR, column c % CPR
+        const uint32_t c = WARP_LOCAL ? (tid >> 5) * (32 * G::CPR) + i * 32 + (tid & 31) : i * G::TPP + tid;
+        uint4 *dst = sm + (c / G::CPR) * G::PITCH4 + (c % G::CPR);
+        if constexpr (ASYNC)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(g4 + c) : "memory");
+        else
+            v[i] = ld_stream(g4 + c);
+    }
+    if constexpr (ASYNC) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) {
+            const uint32_t c = WARP_LOCAL ? (tid >> 5) * (32 * G::CPR) + i * 32 + (tid & 31) : i * G::TPP + tid;
+            sm[(c / G::CPR) * G::PITCH4 + (c % G::CPR)] = v[i];
+        }
+    }
+    if constexpr (WARP_LOCAL) __syncwarp(); else poly_sync<G::TPP>();
+}
+
 // ---------------------------------------------------------------------------------- results by TMA tensor store
 // Forward results leave the SM as E/32 asynchronous tensor stores issued by ONE thread instead of 16 x (LDS.128 +
 // STG.128) per thread.  Every thread writes its row into DENSE shared-memory tiles -- one per 32-word half of the rows,
@@ -233,7 +273,6 @@ __device__ __forceinline__ void global_to_smem(uint4 *sm, const uint32_t *g, uin
 // been READ.  The tiles must start on a 1024-byte boundary (the swizzle is a function of address bits 7..9).
 // Measured and not kept (profiles/r01_experiments.md): the same tiles for the transpose as well, tensor LOADS for the
 // inverse kernel's input, tensor stores for its output.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -519,9 +558,14 @@ ntt_inv_loop_kernel(uint32_t *__restrict__ data, KParams p, uint32_t T) {
     uint32_t *g = data + (size_t)poly * G::N;
 
     uint32_t x[G::E];
+#if AGX_INV_INPUT == 0
     global_to_smem<LOGN, LE>(sm, g, tid);
     prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
     poly_sync<G::TPP>();
+#else
+    prefetch_ahead<LOGN, G::TPP>(g, poly, T, tid);
+    inv_stage_input<LOGN, LE>(sm, g, tid);
+#endif
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         PassAddr a;
