@@ -240,26 +240,26 @@ __device__ __forceinline__ void inv_stage_input(uint4 *sm, const uint32_t *g, ui
     constexpr int NCH = G::N / 4 / G::TPP;               // 16-byte chunks per thread
     constexpr bool WARP_LOCAL = (AGX_INV_INPUT & 2) != 0 && G::TPP > 32;
     constexpr bool ASYNC = (AGX_INV_INPUT & 1) != 0;
-    const uint4 *g4 = reinterpret_cast<const uint4 *>(g);
-    uint4 v[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; i++) {
-        // chunk index c of the polynomial: row c / CPR, column c % CPR
-        const uint32_t c = WARP_LOCAL ? (tid >> 5) * (32 * G::CPR) + i * 32 + (tid & 31) : i * G::TPP + tid;
-        uint4 *dst = sm + (c / G::CPR) * G::PITCH4 + (c % G::CPR);
-        if constexpr (ASYNC)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(g4 + c) : "memory");
-        else
-            v[i] = ld_stream(g4 + c);
-    }
+    // thread's chunk i is polynomial chunk c0 + i*STEP (row c / CPR, column c % CPR of the image); STEP is a multiple of
+    // CPR, so source and destination are a per-thread base plus a compile-time offset
+    constexpr int STEP = WARP_LOCAL ? 32 : G::TPP;
+    static_assert(STEP % G::CPR == 0, "a step must cover whole image rows");
+    const uint32_t c0 = WARP_LOCAL ? (tid >> 5) * (32 * NCH) + (tid & 31) : tid;
+    const uint4 *src = reinterpret_cast<const uint4 *>(g) + c0;
+    uint4 *dst = sm + (c0 / G::CPR) * G::PITCH4 + (c0 % G::CPR);
     if constexpr (ASYNC) {
+        const uint32_t d32 = smem_u32(dst);
+#pragma unroll
+        for (int i = 0; i < NCH; i++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32 + i * (STEP / G::CPR) * G::PITCH4 * 16), "l"(src + i * STEP)
+                         : "memory");
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
+        uint4 v[NCH];
 #pragma unroll
-        for (int i = 0; i < NCH; i++) {
-            const uint32_t c = WARP_LOCAL ? (tid >> 5) * (32 * G::CPR) + i * 32 + (tid & 31) : i * G::TPP + tid;
-            sm[(c / G::CPR) * G::PITCH4 + (c % G::CPR)] = v[i];
-        }
+        for (int i = 0; i < NCH; i++) v[i] = ld_stream(src + i * STEP);
+#pragma unroll
+        for (int i = 0; i < NCH; i++) dst[i * (STEP / G::CPR) * G::PITCH4] = v[i];
     }
     if constexpr (WARP_LOCAL) __syncwarp(); else poly_sync<G::TPP>();
 }
