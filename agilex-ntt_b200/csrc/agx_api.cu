@@ -1067,8 +1067,9 @@ int agx_ref_fwd_dev(agx_ctx *c, uint32_t N, const uint64_t *d_in, const uint64_t
                     const uint64_t *d_twiddles, const uint64_t *d_precon_twiddles, uint32_t numFrames, void *stream) {
     if (!c || !d_in || !d_in2 || !d_out || !d_twiddles || !d_precon_twiddles) return AGX_E_INVALID;
     if (N < 4 || N > 32768 || (N & (N - 1))) return AGX_E_INVALID;
-    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_in2) | reinterpret_cast<uintptr_t>(d_out)) & 15)
-        return AGX_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_in2) | reinterpret_cast<uintptr_t>(d_out) |
+         reinterpret_cast<uintptr_t>(d_twiddles) | reinterpret_cast<uintptr_t>(d_precon_twiddles)) & 15)
+        return AGX_E_INVALID;                          // frames and tables are read by 16-byte accesses
     // the passes work in place in d_out after the first one, so an input that overlaps it is only safe when it IS it
     if ((d_in != d_out || d_in2 != d_out) && (d_in == d_out || d_in2 == d_out)) return AGX_E_INVALID;
     if (numFrames == 0) return AGX_OK;

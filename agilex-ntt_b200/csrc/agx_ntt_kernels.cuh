@@ -823,31 +823,76 @@ __global__ void __launch_bounds__(256) bitrev_rows_kernel(uint32_t *__restrict__
 //   last pass      : the final 4 stages act on 16 consecutive coefficients (128 B) per thread; a warp stages its
 //                    512 consecutive coefficients through a private padded shared-memory tile so that global
 //                    accesses stay coalesced; includes the final reduction to [0,q) (ntt.cpp:377-393).
+// A/B knobs of the 64-bit butterfly and its twiddle loads (profiles/r02_experiments.md).  AGX_U64_VECTW: 0 = 8-byte twiddle
+// loads everywhere, 1 = 16-byte pairs in the frame kernel's 512-thread instantiation only (N >= 16384: +2-6 %; the smaller
+// CTAs lose up to 7 % to the 32 bytes of spills the pairs cost at 128 registers), 2 = pairs everywhere.
+#ifndef AGX_U64_NEGQ
+#define AGX_U64_NEGQ 1
+#endif
+#ifndef AGX_U64_VECTW
+#define AGX_U64_VECTW 1
+#endif
 __device__ __forceinline__ void ref_bfly_u64(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twice) {
     uint64_t tx = x;
     if (tx >= twice) tx -= twice;                 // ntt.cpp:331-332
     const uint64_t c1 = __umul64hi(y, Wp);        // ntt.cpp:344-358
+#if AGX_U64_NEGQ
+    uint64_t negq;                                // -q through an opaque (pure, hence hoisted and shared) instruction:
+    asm("neg.s64 %0, %1;" : "=l"(negq) : "l"(q)); // left as 0 - q the compiler folds the sum below back into a difference
+    const uint64_t Q = W * y + c1 * negq;         // ntt.cpp:363  W*y - c1*q mod 2^64; written as a sum the second product
+                                                  // accumulates onto the first (ptxas otherwise negates c1 per butterfly:
+                                                  // 25.5 instead of 27.5 SASS instructions, experiments/u64_bfly_variants.cu)
+#else
     const uint64_t Q = W * y - c1 * q;            // ntt.cpp:363
+#endif
     x = tx + Q;                                   // ntt.cpp:368
     y = tx + twice - Q;                           // ntt.cpp:369
 }
 
-template <int LS>
-__device__ __forceinline__ void ref_stages_u64(uint64_t (&x)[1 << LS], const uint64_t *__restrict__ roots,
-                                               const uint64_t *__restrict__ precons, uint32_t s0, uint32_t p_hi, uint64_t q) {
-    const uint64_t twice = q << 1;
+// The 2^j twiddles (and precons) a thread needs at local stage j of a register pass are consecutive table entries starting
+// at an index that is a multiple of 2^j (ntt.cpp:298-300: m + i with m = 2^s >= 2^j groups and i = (group of the pass) << j),
+// so for j >= 1 they come in as 16-byte pairs: half the load instructions of one LDG.64 per entry.  The tables must be
+// 16-byte aligned (cudaMalloc'd ones are; agx_ref_fwd_dev checks the caller's).
+template <int CNT, bool VEC>
+__device__ __forceinline__ void ref_load_tw_u64(uint64_t (&W)[CNT], uint64_t (&Wp)[CNT], const uint64_t *__restrict__ roots,
+                                                const uint64_t *__restrict__ precons, uint32_t tbase) {
+    if constexpr (CNT == 1 || !VEC) {
 #pragma unroll
-    for (int j = 0; j < LS; j++) {
-        constexpr int E = 1 << LS;
-        const int half = E >> (j + 1);
-        const uint32_t tbase = (1u << (s0 + j)) + (p_hi << j);      // roots[m + i]: m = 2^s groups, i = p >> (logN - s)
+        for (int g = 0; g < CNT; g++) {
+            W[g] = __ldg(roots + tbase + g);
+            Wp[g] = __ldg(precons + tbase + g);
+        }
+    } else {
+        const ulonglong2 *r2 = reinterpret_cast<const ulonglong2 *>(roots + tbase);
+        const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(precons + tbase);
 #pragma unroll
-        for (int g = 0; g < (1 << j); g++) {
-            const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
-#pragma unroll
-            for (int i = 0; i < half; i++) ref_bfly_u64(x[g * 2 * half + i], x[g * 2 * half + i + half], W, Wp, q, twice);
+        for (int g2 = 0; g2 < CNT / 2; g2++) {
+            const ulonglong2 a = __ldg(r2 + g2), b = __ldg(p2 + g2);
+            W[2 * g2] = a.x; W[2 * g2 + 1] = a.y;
+            Wp[2 * g2] = b.x; Wp[2 * g2 + 1] = b.y;
         }
     }
+}
+
+// one stage of a register pass over E = 2^LS coefficients: local stage J pairs x[g*2h + i] with x[g*2h + i + h], h = E >> (J+1)
+template <int LS, int J, bool VEC>
+__device__ __forceinline__ void ref_stage_u64(uint64_t (&x)[1 << LS], const uint64_t *__restrict__ roots,
+                                              const uint64_t *__restrict__ precons, uint32_t tbase, uint64_t q, uint64_t twice) {
+    constexpr int half = (1 << LS) >> (J + 1);
+    uint64_t W[1 << J], Wp[1 << J];
+    ref_load_tw_u64<(1 << J), VEC>(W, Wp, roots, precons, tbase);
+#pragma unroll
+    for (int g = 0; g < (1 << J); g++)
+#pragma unroll
+        for (int i = 0; i < half; i++) ref_bfly_u64(x[g * 2 * half + i], x[g * 2 * half + i + half], W[g], Wp[g], q, twice);
+}
+
+template <int LS, int J = 0>
+__device__ __forceinline__ void ref_stages_u64(uint64_t (&x)[1 << LS], const uint64_t *__restrict__ roots,
+                                               const uint64_t *__restrict__ precons, uint32_t s0, uint32_t p_hi, uint64_t q) {
+    // roots[m + i]: m = 2^s groups, i = p >> (logN - s)
+    ref_stage_u64<LS, J, (AGX_U64_VECTW >= 2)>(x, roots, precons, (1u << (s0 + J)) + (p_hi << J), q, q << 1);
+    if constexpr (J + 1 < LS) ref_stages_u64<LS, J + 1>(x, roots, precons, s0, p_hi, q);
 }
 
 template <int LS>
@@ -935,23 +980,15 @@ __global__ void __launch_bounds__(128) ref_u64_last_pass_kernel(uint64_t *data, 
 // coefficients every 17 words of 8 bytes (A(idx) = idx + idx/16), which makes every pass's 64-bit accesses
 // conflict-free: lanes walk along a row when lo >= 4, and down the rows at a 136-byte pitch when lo = 0.
 // Arithmetic: ref_bfly_u64 (ntt.cpp:331-369 mod 2^64, any tables), final reduction ntt.cpp:377-393.
-template <int JFIRST>
+template <bool VEC, int JFIRST, int J = JFIRST>
 __device__ __forceinline__ void ref_pass16_u64(uint64_t (&x)[16], const uint64_t *__restrict__ roots,
                                                const uint64_t *__restrict__ precons, uint32_t s_first, uint32_t t_hi, uint64_t q,
                                                uint64_t twice) {
-    // local stage j (JFIRST..3) is global stage s_first + (j - JFIRST); pairs x[g*2h + i], x[g*2h + i + h], h = 8 >> j;
-    // twiddle index m + i of ntt.cpp:298-300 = 2^s + (t_hi << j) + g
-#pragma unroll
-    for (int j = JFIRST; j < 4; j++) {
-        const int h = 8 >> j;
-        const uint32_t tbase = (1u << (s_first + j - JFIRST)) + (t_hi << j);
-#pragma unroll
-        for (int g = 0; g < (1 << j); g++) {
-            const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
-#pragma unroll
-            for (int i = 0; i < h; i++) ref_bfly_u64(x[g * 2 * h + i], x[g * 2 * h + i + h], W, Wp, q, twice);
-        }
-    }
+    // local stage J (JFIRST..3) is global stage s_first + (J - JFIRST); pairs x[g*2h + i], x[g*2h + i + h], h = 8 >> J;
+    // twiddle index m + i of ntt.cpp:298-300 = 2^s + (t_hi << J) + g  (s_first >= JFIRST in every caller, so the index of
+    // g = 0 is a multiple of 2^J as ref_load_tw_u64 needs)
+    ref_stage_u64<4, J, VEC>(x, roots, precons, (1u << (s_first + J - JFIRST)) + (t_hi << J), q, twice);
+    if constexpr (J < 3) ref_pass16_u64<VEC, JFIRST, J + 1>(x, roots, precons, s_first, t_hi, q, twice);
 }
 
 template <int NT>
@@ -961,6 +998,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
                                                               uint32_t split) {
     // split = 0: one CTA per frame, logn <= 14.  split = 1: two CTAs per frame (logn = 15), CTA parity = which half.
     extern __shared__ uint64_t img[];
+    constexpr bool VEC = AGX_U64_VECTW >= 2 || (AGX_U64_VECTW == 1 && NT >= 512);   // 16-byte twiddle pairs
     const uint32_t tid = threadIdx.x;
     const uint32_t frame = split ? blockIdx.x >> 1 : blockIdx.x, half_id = split ? blockIdx.x & 1u : 0u;
     const uint32_t lg = logn - split;                              // log2 of the coefficients this CTA owns
@@ -993,17 +1031,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
             }
             // this CTA's sub-transform: stage s of it is global stage s + split, group offset half_id << s
             // (roots index = 2^(s+split) + (half_id << s) + local group)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int h = 8 >> j;
-                const uint32_t tbase = (1u << (j + split)) + (half_id << j);
-#pragma unroll
-                for (int g = 0; g < (1 << j); g++) {
-                    const uint64_t W = __ldg(roots + tbase + g), Wp = __ldg(precons + tbase + g);
-#pragma unroll
-                    for (int i = 0; i < h; i++) ref_bfly_u64(x[g * 2 * h + i], x[g * 2 * h + i + h], W, Wp, q, twice);
-                }
-            }
+            ref_pass16_u64<VEC, 0>(x, roots, precons, split, half_id, q, twice);
             uint64_t *s = img + vt + (vt >> 4);
             const uint32_t stride = (1u << lo) + (1u << (lo - 4));
 #pragma unroll
@@ -1026,10 +1054,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
             // twiddle index: 2^(s+split) + ((half_id << s) + group) with group = (t_hi << j) + g at local stage j
             const uint32_t sg = s_done + split;                    // global stage of the first active local stage
             const uint32_t th = t_hi + (half_id << (s_done - jfirst));   // the CTA's half as the top bit of the group index
-            if (jfirst == 0) ref_pass16_u64<0>(x, roots, precons, sg, th, q, twice);
-            else if (jfirst == 1) ref_pass16_u64<1>(x, roots, precons, sg, th, q, twice);
-            else if (jfirst == 2) ref_pass16_u64<2>(x, roots, precons, sg, th, q, twice);
-            else ref_pass16_u64<3>(x, roots, precons, sg, th, q, twice);
+            if (jfirst == 0) ref_pass16_u64<VEC, 0>(x, roots, precons, sg, th, q, twice);
+            else if (jfirst == 1) ref_pass16_u64<VEC, 1>(x, roots, precons, sg, th, q, twice);
+            else if (jfirst == 2) ref_pass16_u64<VEC, 2>(x, roots, precons, sg, th, q, twice);
+            else ref_pass16_u64<VEC, 3>(x, roots, precons, sg, th, q, twice);
 #pragma unroll
             for (int k = 0; k < 16; k++) s[k * stride] = x[k];
         }
@@ -1041,7 +1069,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
         uint64_t *s = img + vt * 17;
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = s[k];
-        ref_pass16_u64<0>(x, roots, precons, s_done + split, vt + (half_id << s_done), q, twice);
+        ref_pass16_u64<VEC, 0>(x, roots, precons, s_done + split, vt + (half_id << s_done), q, twice);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             uint64_t v = x[k];

@@ -152,7 +152,8 @@ int agx_wait(agx_ctx *ctx);
 /* The same transform on DEVICE pointers, asynchronous on `stream` (what the three calls above run per chunk; exposes
  * the kernels' rate without PCIe): frame b reads d_in[b*N .. b*N + N/2) and d_in2[b*N + N/2 .. (b+1)*N)
  * (ntt.cpp:582-591) and writes d_out[b*N .. (b+1)*N) (ntt.cpp:626-633).  d_twiddles / d_precon_twiddles: N words each
- * on the device.  d_out may be the same buffer as d_in AND d_in2 (in place) but must not overlap just one of them.
+ * on the device.  All five device pointers must be 16-byte aligned (AGX_E_INVALID otherwise; cudaMalloc'd buffers are).
+ * d_out may be the same buffer as d_in AND d_in2 (in place) but must not overlap just one of them.
  * Any 64-bit modulus: the arithmetic is the reference's, mod 2^64 (ntt.cpp:147-148, 331-369), so results are the
  * reference's for every modulus it accepts; they are the NTT when q < 2^62 (lazy range [0,4q) inside 64 bits). */
 int agx_ref_fwd_dev(agx_ctx *ctx, uint32_t N, const uint64_t *d_in, const uint64_t *d_in2, uint64_t *d_out,
