@@ -242,6 +242,15 @@ def test_device_pointer_entry_point(A, N, bits):
         p.fwd_dev(N, d_in, d_in2, d_in, q, d_tw, d_pre, frames)
     with pytest.raises(A.AgxError):
         p.fwd_dev(N + 1, d_in, d_in2, d_out, q, d_tw, d_pre, frames)
+    # frames and tables are read by 16-byte accesses: a pointer that is only 8-byte aligned is refused, not faulted on
+    pad = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+    pad[1:] = d_tw
+    with pytest.raises(A.AgxError):
+        p.fwd_dev(N, d_in, d_in2, d_out, q, pad[1:], d_pre, frames)
+    with pytest.raises(A.AgxError):
+        p.fwd_dev(N, d_in, d_in2, d_out, q, d_tw, pad[1:], frames)
+    p.fwd_dev(N, d_in, d_in2, d_out, q, d_tw, d_pre, frames)          # the context still works after the refusals
+    torch.cuda.synchronize()
     p.close()
 
 
