@@ -32,6 +32,10 @@ def _load() -> C.CDLL:
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the CUDA extension is mandatory; there is no CPU fallback)")
+    if "AGX_LIB" not in os.environ and _build.recorded_hash() not in (None, _build.source_hash()):
+        import warnings
+        warnings.warn(f"{path} was built from other sources than the ones in csrc/: rebuild with "
+                      "`python -c 'import __graft_entry__ as g; g.build()'`", RuntimeWarning, stacklevel=3)
     L = C.CDLL(path)
     vp = C.c_void_p
     sigs = {

@@ -48,12 +48,34 @@ def _run(cmd: list[str]) -> None:
         raise RuntimeError("build failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout[-4000:], r.stderr[-4000:]))
 
 
+def source_hash() -> str:
+    """SHA-256 over the library's sources (names and contents): what `lib/libagxntt.so.srchash` records at build time."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(_sources(CSRC) + [os.path.join(ROOT, "include", "agxntt.h")]):
+        h.update(os.path.relpath(f, ROOT).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def recorded_hash() -> str | None:
+    try:
+        with open(LIB + ".srchash") as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def build_lib(force: bool = False) -> str:
     deps = _sources(CSRC) + [os.path.join(ROOT, "include", "agxntt.h")]
-    if force or _stale(LIB, deps):
+    want = source_hash()
+    if force or _stale(LIB, deps) or recorded_hash() != want:      # mtimes lie after a checkout; the hash does not
         os.makedirs(LIBDIR, exist_ok=True)
         _run([nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB,
                                       os.path.join(CSRC, "agx_api.cu"), os.path.join(CSRC, "agx_tables.cpp")])
+        with open(LIB + ".srchash", "w") as fh:
+            fh.write(want + "\n")
     return LIB
 
 
