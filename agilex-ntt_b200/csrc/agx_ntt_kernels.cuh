@@ -841,7 +841,7 @@ __device__ __forceinline__ void ref_bfly_u64(uint64_t &x, uint64_t &y, uint64_t 
     asm("neg.s64 %0, %1;" : "=l"(negq) : "l"(q)); // left as 0 - q the compiler folds the sum below back into a difference
     const uint64_t Q = W * y + c1 * negq;         // ntt.cpp:363  W*y - c1*q mod 2^64; written as a sum the second product
                                                   // accumulates onto the first (ptxas otherwise negates c1 per butterfly:
-                                                  // 25.5 instead of 27.5 SASS instructions, experiments/u64_bfly_variants.cu)
+                                                  // 25.5 instead of 27.5 SASS instructions, profiles/r02_experiments.md)
 #else
     const uint64_t Q = W * y - c1 * q;            // ntt.cpp:363
 #endif
