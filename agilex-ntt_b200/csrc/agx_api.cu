@@ -590,11 +590,15 @@ int ref_launch(agx_ctx *c, uint32_t logn, const uint64_t *d_in, const uint64_t *
     static const bool passes_only = getenv("AGX_REF_PASSES") != nullptr;   // ... the multi-launch pass kernels
     // One launch, frame resident in shared memory (two CTAs per frame at N = 32768, which is unsafe in place: the CTA of
     // one half would overwrite what the other has not read yet).  Splitting N = 16384 the same way -- two independent
-    // 8192-point halves per SM instead of one 136 KB CTA -- measured +5 % on a 1 GiB batch and -5 % on a 16 MiB chunk:
-    // not done.
+    // 8192-point halves per SM instead of one 136 KB CTA, which cover each other's barriers and load phases -- measured
+    // +5 % on a 1 GiB batch and -5 % on a 16 MiB chunk (less than a wave of CTAs either way), so it is done for batches of
+    // at least two waves of whole-frame CTAs when the output is a separate buffer (AGX_REF_SPLIT14=0 / 1: never / always).
     const bool in_place = d_out == d_in || d_out == d_in2;
+    static const char *split14_env = getenv("AGX_REF_SPLIT14");
+    const bool split14 = logn == 14 && !in_place &&
+                         (split14_env ? split14_env[0] == '1' : frames >= (size_t)2 * (size_t)c->sms);
     if (logn >= 10 && !naive && !passes_only && !(logn == 15 && in_place)) {
-        const uint32_t split = logn == 15 ? 1u : 0u, lg = logn - split;
+        const uint32_t split = (logn == 15 || split14) ? 1u : 0u, lg = logn - split;
         const size_t smem = ((size_t)17 << (lg - 4)) * 8;
         const unsigned grid = (unsigned)(frames << split);
         // N/32 threads per CTA, two virtual threads each (512 at N = 16384, the largest frame an SM holds): below that

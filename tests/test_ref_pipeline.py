@@ -254,6 +254,33 @@ def test_device_pointer_entry_point(A, N, bits):
     p.close()
 
 
+def test_device_pointer_entry_point_large_batch_two_ctas_per_frame(A):
+    """N = 16384 with at least two waves of frames and a separate output runs two CTAs per frame (each an 8192-point half
+    after its own copy of stage 0, as N = 32768 always does); in place it must keep one CTA per frame.  Both against the
+    restatement, lazy inputs, in2 != in."""
+    import torch
+    N, q = 16384, O.U64_PRIMES[60]
+    tw, pre = O.tables_u64(N, q)
+    frames = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 5
+    x, x2 = O.synthetic_u64(N * frames, 5, 4 * q), O.synthetic_u64(N * frames, 6, 4 * q)
+    want = O.batch_ref_fwd_u64(N, np.concatenate([a for f in range(frames) for a in
+                                                   (x[f * N: f * N + N // 2], x2[f * N + N // 2: (f + 1) * N])]),
+                               q, tw, pre, threads=O.max_threads())
+    dev = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    d_in, d_in2, d_tw, d_pre = dev(x), dev(x2), dev(tw), dev(pre)
+    d_out = torch.zeros_like(d_in)
+    p = A.RefPipeline()
+    p.fwd_dev(N, d_in, d_in2, d_out, q, d_tw, d_pre, frames)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().view(np.uint64) == want).all()
+    assert (d_in.cpu().numpy().view(np.uint64) == x).all() and (d_in2.cpu().numpy().view(np.uint64) == x2).all()
+    same = O.batch_ref_fwd_u64(N, x.copy(), q, tw, pre, threads=O.max_threads())
+    p.fwd_dev(N, d_in, d_in, d_in, q, d_tw, d_pre, frames)            # in place: one CTA per frame
+    torch.cuda.synchronize()
+    assert (d_in.cpu().numpy().view(np.uint64) == same).all()
+    p.close()
+
+
 def test_buffer_size_contract_is_checked(A):
     """agx_ref_* take bare pointers, so the mirrors of ntt_input_kernel / ntt_output_kernel check that the
     buffers describe numFrames x N (main.cpp:26-37) before anything is handed to the DMA engines."""
