@@ -84,3 +84,56 @@ def test_random_parameters_against_the_oracle(A, torch, logn, primes, B, root_pi
         c.polymul(dc, dev(x), dev(z))
         assert (back(dc) == P.polymul(x.copy(), z.copy())).all(), "product"
     c.close()
+
+
+def _u64_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(count):
+        logn = int(rng.choice([2, 3, 5, 8, 9, 10, 10, 11, 12, 13, 13, 14, 14, 15]))
+        frames = int(rng.integers(1, 7))
+        kind = int(rng.integers(0, 3))       # 0: NTT prime + real tables, 1: arbitrary modulus + arbitrary tables, 2: tiny modulus
+        out.append(pytest.param(logn, frames, kind, int(rng.integers(1, 1 << 30)), id=f"{i}-N{1 << logn}-f{frames}-k{kind}"))
+    return out
+
+
+@pytest.mark.parametrize("logn,frames,kind,seed", _u64_cases(40, 20261019))
+def test_random_u64_frames_against_the_restatement(A, torch, logn, frames, kind, seed):
+    """The reference-shaped u64 path claims the reference's arithmetic bit for bit for ANY modulus and ANY tables
+    (ntt.cpp:147-148, 331-369 wrap mod 2^64; main.cpp:46-55 itself feeds tables that are not Shoup pairs): random sizes,
+    frame counts, in2 != in, separate and in-place output, on (0) NTT primes with real tables and lazy inputs, (1) arbitrary
+    64-bit moduli with arbitrary 64-bit table entries and inputs, (2) a tiny modulus."""
+    N = 1 << logn
+    rng = np.random.default_rng(seed)
+    full = lambda size: rng.integers(0, 1 << 63, size=size, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=size, dtype=np.uint64)
+    if kind == 0:
+        q = O.U64_PRIMES[int(rng.choice([50, 60, 62, 63]))]
+        tw, pre = O.tables_u64(N, q)
+        x, x2 = O.synthetic_u64(N * frames, seed, 4 * q if q < (1 << 62) else q), O.synthetic_u64(N * frames, seed + 1, q)
+    elif kind == 1:
+        q = int(full(1)[0]) | 1
+        tw, pre, x, x2 = full(N), full(N), full(N * frames), full(N * frames)
+    else:
+        q = 65537
+        tw, pre = full(N) % np.uint64(q), full(N)
+        x, x2 = full(N * frames) % np.uint64(4 * q), full(N * frames) % np.uint64(4 * q)
+    want = O.ref_fwd_u64(x, x2, q, tw, pre, frames)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    d_in, d_in2, d_tw, d_pre = dev(x), dev(x2), dev(tw), dev(pre)
+    d_out = torch.zeros_like(d_in)
+    p = A.RefPipeline()
+    p.fwd_dev(N, d_in, d_in2, d_out, q, d_tw, d_pre, frames)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().view(np.uint64) == want).all(), "separate output"
+    want_same = O.ref_fwd_u64(x, x, q, tw, pre, frames)
+    p.fwd_dev(N, d_in, d_in, d_in, q, d_tw, d_pre, frames)
+    torch.cuda.synchronize()
+    assert (d_in.cpu().numpy().view(np.uint64) == want_same).all(), "in place"
+    # and through the three reference-named calls on host buffers (main.cpp:60-74)
+    out = np.zeros(N * frames, dtype=np.uint64)
+    p.ntt_input_kernel(x, x2, np.array([q], dtype=np.uint64), tw, pre, frames)
+    p.fwd_ntt_kernel(0)
+    p.ntt_output_kernel(out, frames)
+    p.wait()
+    assert (out == want).all(), "host pipeline"
+    p.close()
