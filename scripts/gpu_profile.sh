@@ -20,6 +20,10 @@ timeout 300 python profiles/prof_run.py --n 2048 --polymul > gpurun_out/plain_pm
     timeout 900 $NCU -k regex:'ntt_' -s 3 -c 3 -o gpurun_out/prof_r02_polymul python profiles/prof_run.py --n 2048 --polymul > gpurun_out/ncu_pm.log 2>&1
 timeout 300 python profiles/prof_u64.py > gpurun_out/plain_u64.log 2>&1 && \
     timeout 900 $NCU -k regex:'ref_u64' -s 1 -c 1 -o gpurun_out/prof_r02_u64 python profiles/prof_u64.py > gpurun_out/ncu_u64.log 2>&1
+for nn in 1024 2048; do
+  timeout 300 python profiles/prof_run.py --n $nn > gpurun_out/plain_n$nn.log 2>&1 && \
+    timeout 900 $NCU -k regex:'ntt_' -s 4 -c 2 -o gpurun_out/prof_r02_n$nn python profiles/prof_run.py --n $nn > gpurun_out/ncu_n$nn.log 2>&1
+done
 tail -n 2 gpurun_out/plain.log gpurun_out/plain_pm.log gpurun_out/plain_u64.log gpurun_out/pytest_gpu.txt
 python - <<'PY'
 import json

@@ -5,6 +5,9 @@ cd "$(dirname "$0")/.."
 python profiles/summarize_ncu.py gpurun_out/prof_r02_final.ncu-rep > profiles/r02_final_ncu_summary.md
 python profiles/summarize_ncu.py gpurun_out/prof_r02_polymul.ncu-rep > profiles/r02_polymul_n2048_ncu_summary.md
 python profiles/summarize_ncu.py gpurun_out/prof_r02_u64.ncu-rep > profiles/r02_u64_frame_ncu_summary.md
+for nn in 1024 2048; do
+  [ -f gpurun_out/prof_r02_n$nn.ncu-rep ] && python profiles/summarize_ncu.py gpurun_out/prof_r02_n$nn.ncu-rep > profiles/r02_n${nn}_ncu_summary.md
+done
 cp gpurun_out/r02_launches.csv profiles/r02_final_launches.csv
 cp gpurun_out/bench.json profiles/r02_c_bench_1gpu.json
 cp gpurun_out/bench_reference.json profiles/r02_c_bench_reference.json
