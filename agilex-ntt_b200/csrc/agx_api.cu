@@ -79,6 +79,7 @@ struct agx_ctx {
     LimbConst *d_lc = nullptr;
     LimbConst lc0 = {};                                    // limb 0, passed by value in the kernel parameters
     bool r16 = false;                                      // AGX_WITH_R16 builds only
+    bool big = false;                                      // n >= 8192 (u32): ntt_big_kernel instead of the radix-2 kernel
 #if AGX_WITH_R16
     uint2 *d_tw16_fwd = nullptr, *d_tw16_inv = nullptr, *d_u16_fwd = nullptr, *d_u16_inv = nullptr;
     uint2 u16_fwd0[kR16UInv] = {}, u16_inv0[kR16UInv] = {};   // limb 0's uniform twiddles, passed by value
@@ -329,15 +330,29 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     return (int)cudaGetLastError();
 }
 
+// one transform per (polynomial, limb) row of `d`, in place, at a size outside {1024, 2048, 4096}: n >= 8192 through the
+// register-radix passes of ntt_big_kernel, smaller sizes (and AGX_GENERIC_ONLY=1) through the radix-2 kernel
+void launch_generic_ntt(agx_ctx *c, bool inverse, uint32_t *d, size_t T, cudaStream_t s) {
+    const uint2 *tw = inverse ? c->d_tw_inv : c->d_tw_fwd;
+    if (c->big) {
+        const size_t smem = ((size_t)c->n + c->n / 32) * 4;
+        const unsigned threads = c->logn <= 14 ? 512 : 1024;   // two CTAs per SM cover each other's barriers where they fit
+        if (inverse) ntt_big_kernel<true><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
+        else ntt_big_kernel<false><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
+    } else {
+        const size_t smem = (size_t)c->n * 4;
+        const unsigned threads = c->n / 2 < 256 ? (c->n / 2 < 32 ? 32 : c->n / 2) : 256;
+        if (inverse) ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
+        else ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
+    }
+    c->launches++;
+}
+
 int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t T, cudaStream_t s) {
-    const size_t smem = (size_t)c->n * 4;
-    const unsigned threads = c->n / 2 < 256 ? (c->n / 2 < 32 ? 32 : c->n / 2) : 256;
     if (op == OP_FWD) {
-        ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
-        c->launches++;
+        launch_generic_ntt(c, false, out, T, s);
     } else if (op == OP_INV) {
-        ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
-        c->launches++;
+        launch_generic_ntt(c, true, out, T, s);
     } else {
         // generic sizes: out <- NTT(a), tmp <- NTT(b) in a stream-ordered scratch buffer, out <- INTT(out .* tmp).
         // Every aliasing case of the fast path is served: the product commutes (out == b), squaring needs no scratch.
@@ -351,11 +366,11 @@ int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const ui
             if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, b, bytes, cudaMemcpyDeviceToDevice, s);
         }
         if (e == cudaSuccess) {
-            ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_fwd, c->d_lc, c->L, c->logn);
-            if (tmp) ntt_generic_kernel<false><<<(unsigned)T, threads, smem, s>>>(tmp, c->d_tw_fwd, c->d_lc, c->L, c->logn);
+            launch_generic_ntt(c, false, out, T, s);
+            if (tmp) launch_generic_ntt(c, false, tmp, T, s);
             pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, tmp ? tmp : out, c->d_lc, c->L, c->logn, total);
-            ntt_generic_kernel<true><<<(unsigned)T, threads, smem, s>>>(out, c->d_tw_inv, c->d_lc, c->L, c->logn);
-            c->launches += tmp ? 4 : 3;
+            c->launches++;
+            launch_generic_ntt(c, true, out, T, s);
             e = cudaGetLastError();
         }
         if (tmp) { const cudaError_t ef = cudaFreeAsync(tmp, s); if (e == cudaSuccess) e = ef; }   // freed on every path
@@ -787,6 +802,8 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
     {
         cudaError_t e = cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         const int frame_smem = 17 * 1024 * 8;                          // N = 16384 image: 136 KB
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
@@ -807,6 +824,7 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
         c->has_parms = true;
         c->n = parms->n; c->logn = parms->logn; c->L = parms->nlimbs;
         c->le = select_le(c->logn);
+        c->big = c->le == 0 && c->logn >= 13 && getenv("AGX_GENERIC_ONLY") == nullptr;   // A/B and test knob: the radix-2 kernel
 #if AGX_WITH_R16
         {   // n = 4096: radix-16 three-pass kernels (they need the TMA tensor-map encoder), selected with AGX_KERNEL=r16
             const char *k = getenv("AGX_KERNEL");
@@ -1157,6 +1175,7 @@ int agx_variant(const agx_ctx *c, char *buf, size_t buflen) {
     if (!c->has_parms) snprintf(buf, buflen, "ref_u64");
     else if (c->r16) snprintf(buf, buflen, "ntt_r16<%u>", c->logn);
     else if (c->le) snprintf(buf, buflen, "ntt2p<%u,%d>", c->logn, c->le);
+    else if (c->big) snprintf(buf, buflen, "ntt_big<%u>", c->logn);
     else snprintf(buf, buflen, "generic");
     return AGX_OK;
 }

@@ -706,6 +706,136 @@ __global__ void __launch_bounds__(256) ntt_generic_kernel(uint32_t *__restrict__
     }
 }
 
+// ------------------------------------------------------------------- large sizes (n = 8192, 16384, 32768), u32
+// Above the two-pass kernels' reach a polynomial (32-128 KB) no longer fits the register files of one CTA's threads, but it
+// fits ONE CTA's shared memory, so it is still read from HBM once and written once.  The log2 n stages (ntt.cpp:146-159 loop
+// nest, :292-300 twiddle index m + i) run as passes of up to four stages on 16 coefficients per (virtual) thread -- the
+// scheme of the u64 frame kernel below, with the u32 butterflies of agx_arith.cuh and natural-order tables:
+//   pass 0 works on index bits [logn-4, logn), the next ones on the four bits below, ... (the last of those may be partial:
+//   it then holds bits [4,8) and runs only the stages of the bits not yet done), a final pass on bits 3..0.
+// Pass p is described by (lo, jf, sf): element k of virtual thread vt = (t_hi, t_lo) is index (t_hi << (lo+4)) + t_lo + (k << lo),
+// local stages jf..3 are global stages sf.., stage j pairs x[g*2h+i] with x[g*2h+i+h], h = 8 >> j, under twiddle
+// tw[2^(sf+j-jf) + (t_hi << j) + g].  The inverse runs the same passes backwards with Gentleman-Sande butterflies on the same
+// indices of the inverse table and multiplies by n^-1 (entry 0 of that table) on the way out.
+// Image in shared memory: one word of padding per 32 (A(idx) = idx + idx/32): conflict-free when lanes walk along
+// consecutive indices (lo >= 5) and when every lane reads its own 16 consecutive words (lo = 0).
+__device__ __forceinline__ uint32_t big_img(uint32_t idx) { return idx + (idx >> 5); }
+
+template <bool INVERSE, int JF>
+__device__ __forceinline__ void big_pass16(uint32_t (&x)[16], const uint2 *__restrict__ tw, uint32_t sf, uint32_t t_hi,
+                                           const LimbConst &c) {
+#pragma unroll
+    for (int jj = JF; jj < 4; jj++) {
+        const int j = INVERSE ? 3 + JF - jj : jj;              // forward JF..3, inverse 3..JF
+        const int h = 8 >> j;
+        const uint32_t tbase = (1u << (sf + j - JF)) + (t_hi << j);
+        uint2 w[8];
+        if (j == 0) {
+            w[0] = __ldg(tw + tbase);
+        } else {                                             // 2^j consecutive entries from a 2^j-aligned index: 16-byte pairs
+            const uint4 *t4 = reinterpret_cast<const uint4 *>(tw + tbase);
+#pragma unroll
+            for (int g2 = 0; g2 < (1 << j) / 2; g2++) {
+                const uint4 v = __ldg(t4 + g2);
+                w[2 * g2] = make_uint2(v.x, v.y);
+                w[2 * g2 + 1] = make_uint2(v.z, v.w);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < (1 << j); g++)
+#pragma unroll
+            for (int i = 0; i < h; i++) {
+                if (INVERSE) gs_bfly(x[g * 2 * h + i], x[g * 2 * h + i + h], w[g], c);
+                else ct_bfly(x[g * 2 * h + i], x[g * 2 * h + i + h], w[g], c);
+            }
+    }
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ void big_pass16_jf(uint32_t (&x)[16], const uint2 *__restrict__ tw, uint32_t jf, uint32_t sf,
+                                              uint32_t t_hi, const LimbConst &c) {
+    if (jf == 0) big_pass16<INVERSE, 0>(x, tw, sf, t_hi, c);
+    else if (jf == 1) big_pass16<INVERSE, 1>(x, tw, sf, t_hi, c);
+    else if (jf == 2) big_pass16<INVERSE, 2>(x, tw, sf, t_hi, c);
+    else big_pass16<INVERSE, 3>(x, tw, sf, t_hi, c);
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(1024, 1) ntt_big_kernel(uint32_t *data, const uint2 *__restrict__ tw_nat,
+                                                           const LimbConst *__restrict__ lc, uint32_t L, uint32_t logn) {
+    extern __shared__ uint32_t bimg[];
+    const uint32_t n = 1u << logn, vthreads = n >> 4, tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t poly = blockIdx.x, limb = poly % L;
+    const LimbConst c = lc[limb];
+    const uint2 *tw = tw_nat + (size_t)limb * n;
+    uint32_t *g = data + (size_t)poly * n;
+    const int np = 2 + (int)((logn - 8 + 3) / 4);              // pass 0, the passes on the bits between, the final pass
+    uint32_t x[16];
+
+    for (int pp = 0; pp < np; pp++) {
+        const int p = INVERSE ? np - 1 - pp : pp;
+        uint32_t lo, jf, sf;
+        if (p == 0) { lo = logn - 4; jf = 0; sf = 0; }
+        else if (p == np - 1) { lo = 0; jf = 0; sf = logn - 4; }
+        else {
+            const uint32_t rem = logn - 8 - 4 * (uint32_t)(p - 1);
+            lo = rem >= 4 ? rem : 4; jf = rem >= 4 ? 0 : 4 - rem; sf = 4 + 4 * (uint32_t)(p - 1);
+        }
+        // the first pass of either direction reads global memory, the last one writes it: pass 0 by coalesced 4-byte
+        // accesses (lanes on consecutive indices), the final pass by four 16-byte accesses of a thread's own 64 bytes
+        const bool from_global = pp == 0, to_global = pp == np - 1;
+        // Image address of element k: A(idx0 + (k << lo)) = A(idx0) + k * stride + fix(k), all of it a per-thread base plus
+        // uniform or compile-time terms: lo >= 5: k << lo is a multiple of 32, stride = 2^lo + 2^(lo-5), fix = 0;
+        // lo == 4 (idx0 % 256 < 16): stride = 16, fix = k >> 1;  lo == 0 (idx0 % 16 == 0): stride = 1, fix = 0.
+        const uint32_t stride = lo >= 5 ? (1u << lo) + (1u << (lo - 5)) : (1u << lo);
+        for (uint32_t vt = tid; vt < vthreads; vt += NT) {
+            const uint32_t t_lo = vt & ((1u << lo) - 1), t_hi = vt >> lo;
+            const uint32_t idx0 = (t_hi << (lo + 4)) + t_lo;
+            uint32_t *sp = bimg + big_img(idx0);
+            if (from_global && INVERSE) {                      // final pass first: lo == 0
+                const uint4 *g4 = reinterpret_cast<const uint4 *>(g + idx0);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const uint4 v = g4[k4];
+                    x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w;
+                }
+            } else if (from_global) {
+                const uint32_t *gp = g + idx0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = __ldcs(gp + ((uint32_t)k << lo));
+            } else if (lo == 4) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = sp[16 * k + (k >> 1)];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = sp[k * stride];
+            }
+            big_pass16_jf<INVERSE>(x, tw, jf, sf, t_hi, c);
+            if (!INVERSE && p == np - 1) {                     // ntt.cpp:377-393
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = reduce4q(x[k], c);
+            }
+            if (to_global && INVERSE) {                        // pass 0 last: scale by n^-1, coalesced 4-byte stores
+                const uint2 wn = __ldg(tw);                    // the inverse table keeps (n^-1, .) in its unused entry 0
+                uint32_t *gp = g + idx0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) __stcs(gp + ((uint32_t)k << lo), csub(shoup_mul(x[k], wn, c.negq), c.negq));
+            } else if (to_global) {                            // final pass last: lo == 0
+                uint4 *g4 = reinterpret_cast<uint4 *>(g + idx0);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) g4[k4] = make_uint4(x[4 * k4], x[4 * k4 + 1], x[4 * k4 + 2], x[4 * k4 + 3]);
+            } else if (lo == 4) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) sp[16 * k + (k >> 1)] = x[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) sp[k * stride] = x[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256) pointwise_generic_kernel(uint32_t *a, const uint32_t *b,   // a may equal b (squaring)
                                                                 const LimbConst *__restrict__ lc, uint32_t L,

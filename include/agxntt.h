@@ -99,7 +99,8 @@ int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
  * every size.  n = 1024: forward(a), forward(b), pointwise product and inverse run in ONE launch (3 streams of HBM
  * traffic); n = 2048 and 4096: three launches (c = NTT(a); c = NTT(b) .* c; c = INTT(c) -- 7 streams, no scratch
  * memory; the product is bound by the integer-multiply pipe, not by that traffic: DESIGN.md s.4); other sizes: the
- * generic kernels, with a stream-ordered scratch buffer unless a == b. */
+ * transforms of that size (n >= 8192: shared-memory-resident register passes; n <= 512: the generic kernel) around a
+ * pointwise launch, with a stream-ordered scratch buffer unless a == b. */
 int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
 
 /* ---- limb-wise element-wise arithmetic on [B][L][n] DEVICE data (the operations callers run around the transforms,

@@ -619,6 +619,40 @@ def test_forward_without_tensor_store(A, torch, monkeypatch, n):
         c.close()
 
 
+@pytest.mark.parametrize("n", [8192, 16384, 32768])
+def test_large_sizes_register_pass_kernel_and_radix2_kernel_agree(A, torch, monkeypatch, n):
+    """n >= 8192 runs ntt_big_kernel (the polynomial resident in one CTA's shared memory, passes of four stages on 16
+    coefficients per thread); AGX_GENERIC_ONLY=1 at context creation selects the radix-2 kernel instead.  Both must give the
+    oracle's spectra, inverses of arbitrary vectors, round trips and products, on 1 and 3 limbs, ragged batches."""
+    primes = [q for q in (1053818881, 1054212097, 1055260673) if (q - 1) % (2 * n) == 0]
+    for L in (1, len(primes)):
+        P = O.Plan(n, primes[:L])
+        x, z = P.synthetic(5, seed=31), P.synthetic(5, seed=32)
+        want_f, want_i, want_p = P.fwd(x.copy()), P.inv(z.copy()), P.polymul(x.copy(), z.copy())
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("AGX_GENERIC_ONLY", "1")
+            else:
+                monkeypatch.delenv("AGX_GENERIC_ONLY", raising=False)
+            c = A.Context(n, primes[:L])
+            assert c.variant() == ("generic" if generic else f"ntt_big<{n.bit_length() - 1}>")
+            d = to_dev(torch, x)
+            c.fwd(d)
+            assert (to_np(d).reshape(x.shape) == want_f).all(), (generic, "forward")
+            c.inv(d)
+            assert (to_np(d).reshape(x.shape) == x).all(), (generic, "round trip")
+            dz = to_dev(torch, z)
+            c.inv(dz)
+            assert (to_np(dz).reshape(z.shape) == want_i).all(), (generic, "inverse")
+            lazy = to_dev(torch, (x.astype(np.uint64) + np.array(primes[:L], dtype=np.uint64).reshape(1, L, 1)).astype(np.uint32))
+            c.fwd(lazy)
+            assert (to_np(lazy).reshape(x.shape) == want_f).all(), (generic, "lazy inputs")
+            dc = torch.empty_like(d)
+            c.polymul(dc, to_dev(torch, x), to_dev(torch, z))
+            assert (to_np(dc).reshape(x.shape) == want_p).all(), (generic, "product")
+            c.close()
+
+
 @pytest.mark.parametrize("n", [64, 1024, 4096, 32768])
 def test_bitrev_adapter_gives_the_textbook_order(A, torch, n):
     """agx_bitrev permutes each polynomial by bit reversal in place: forward + bitrev is the natural-order spectrum
