@@ -397,6 +397,13 @@ __host__ __device__ constexpr int inv_fold_mask(int J) {   // index bits that ma
     return J < kInvFold ? m : 0;
 }
 
+// AGX_TW_INTERLEAVE: the two twiddles of a 16-byte table slot are stored word-interleaved, (w0, w1, w0', w1') instead of
+// (w0, w0', w1, w1').  A 16-byte load fills four consecutive registers, and the register file has two banks by register
+// parity: with (w, w') in an even/odd pair one of the butterfly's two multiplies y*w, hi(y*w') always reads both of its
+// operands from y's bank; interleaved, both words of a twiddle share a parity and ptxas can keep y in the other bank.
+#ifndef AGX_TW_INTERLEAVE
+#define AGX_TW_INTERLEAVE 1
+#endif
 template <int LOGN, int LE, int J>
 __device__ __forceinline__ void load_tw_generic(uint2 (&w)[1 << J], const PassAddr &a) {
     constexpr int LT = LOGN - LE, TPP = 1 << LT;
@@ -406,8 +413,13 @@ __device__ __forceinline__ void load_tw_generic(uint2 (&w)[1 << J], const PassAd
 #pragma unroll
         for (int h = 0; h < (1 << (J - 1)); h++) {
             const uint4 v = ld_twiddle(a.b4 + ((1 << (LT + J - 1)) + h * TPP));
+#if AGX_TW_INTERLEAVE
+            w[2 * h] = make_uint2(v.x, v.z);
+            w[2 * h + 1] = make_uint2(v.y, v.w);
+#else
             w[2 * h] = make_uint2(v.x, v.y);
             w[2 * h + 1] = make_uint2(v.z, v.w);
+#endif
         }
     }
 }
@@ -1237,6 +1249,19 @@ struct TableSet {
 
 __device__ __forceinline__ uint2 shoup_pair(uint32_t w, uint32_t q) { return make_uint2(w, (uint32_t)(((uint64_t)w << 32) / q)); }
 
+// entry `pos` of a kernel-order table; `vec4`: the slot is fetched by the kernels' 16-byte loads (see AGX_TW_INTERLEAVE)
+__device__ __forceinline__ void store_tw(uint2 *tab, uint32_t pos, uint2 v, bool vec4) {
+#if AGX_TW_INTERLEAVE
+    if (vec4) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(tab) + (pos >> 1) * 4 + (pos & 1);
+        w[0] = v.x;
+        w[2] = v.y;
+        return;
+    }
+#endif
+    tab[pos] = v;
+}
+
 __device__ __forceinline__ void place_table_entry(const TableSet &t, uint32_t k, uint32_t r, bool inverse, uint32_t q,
                                                   uint32_t n_inv, uint32_t logn, int le) {
     const uint2 natural = shoup_pair(r, q);
@@ -1251,15 +1276,15 @@ __device__ __forceinline__ void place_table_entry(const TableSet &t, uint32_t k,
         const uint32_t T = rr / c, kk = rr % c;
         pos = c == 1 ? (1u << s) + T : (1u << s) + ((kk >> 1) * tpp + T) * 2 + (kk & 1);   // = tw_pos<LOGN,LE>(s, T, kk)
     }
-    t.tw[pos] = shoup_pair(w, q);
+    store_tw(t.tw, pos, shoup_pair(w, q), le && pos >= (2u << ((int)logn - le)));   // stages read by 16-byte loads
     if (le && k >= 1 && k < (1u << le)) {   // column pass: local stage j, group gq sits where the row pass of thread 0 looks
         const int j = 31 - __clz(k), lt = (int)logn - le;
         const uint32_t gq = k - (1u << j), tpp = 1u << lt;
         const uint32_t cpos = j == 0 ? tpp : 2 * ((1u << (lt + j - 1)) + (gq >> 1) * tpp) + (gq & 1);
         uint2 cval = natural;
         if (inverse && j >= 1 && j <= kInvFold) cval = shoup_pair(mulmod_dev(r, n_inv, q), q);   // variant A carries n^-1
-        t.twc[cpos] = cval;
-        if (inverse && j >= 1) t.twc[cpos + 2] = natural;                 // variant B: one 16-byte slot further
+        store_tw(t.twc, cpos, cval, j >= 1);
+        if (inverse && j >= 1) store_tw(t.twc, cpos + 2, natural, true);  // variant B: one 16-byte slot further
     }
 }
 
