@@ -23,7 +23,8 @@
 // over its blockIdx (clusterlaunchcontrol.try_cancel, answer delivered asynchronously into shared memory on an
 // mbarrier).  The request is issued at the top of an iteration and read half an iteration later, when the staging
 // copy is issued.  A static stride (poly += resident CTAs) loses 15 % instead of gaining: the warps of an SM do not
-// progress at equal rates (11.5k .. 20k clk per polynomial inside one SM, profiles/r02_pers_trace.txt), so
+// progress at equal rates (11.5k .. 20k clk per polynomial inside one SM; round-1 trace of the persistent build, not tracked -- the shipped
+// kernels' phase trace is profiles/r01_phase_trace.txt), so
 // equal shares finish far apart; with work stealing every CTA index is processed exactly once, whether the
 // hardware launches it or a resident CTA steals it, so correctness does not depend on any request succeeding.
 // AGX_PERS_SCHED=0 builds the static-stride variant (grid = resident CTAs, a multiple of L) for comparison.

@@ -1,5 +1,5 @@
-"""Tiny end-to-end exercise of every kernel for compute-sanitizer runs (one tool per gpurun call):
-   compute-sanitizer --tool racecheck python scripts/sanitize_small.py"""
+"""Small-case parity loop over every kernel (written for compute-sanitizer, which is closed on this pool's GPU
+   boxes; run it plain):  python experiments/sanitize_small.py"""
 import os
 import sys
 
