@@ -48,11 +48,13 @@ def _load() -> C.CDLL:
         "agx_ntt_fwd": [vp, vp, C.c_size_t, vp],
         "agx_ntt_inv": [vp, vp, C.c_size_t, vp],
         "agx_polymul": [vp, vp, vp, vp, C.c_size_t, vp],
+        "agx_polymul_by_spectrum": [vp, vp, vp, vp, C.c_size_t, vp],
         "agx_elementwise": [vp, C.c_int, vp, vp, vp, C.c_size_t, vp],
         "agx_bitrev": [vp, vp, C.c_size_t, vp],
         "agx_ntt_fwd_host": [vp, vp, vp, C.c_size_t],
         "agx_ntt_inv_host": [vp, vp, vp, C.c_size_t],
         "agx_polymul_host": [vp, vp, vp, vp, C.c_size_t],
+        "agx_polymul_by_spectrum_host": [vp, vp, vp, vp, C.c_size_t],
         "agx_host_alloc": [C.POINTER(vp), C.c_size_t],
         "agx_host_free": [vp],
         "agx_fill_synthetic": [vp, vp, C.c_size_t, C.c_uint64, C.c_size_t, vp],
@@ -75,7 +77,7 @@ def _load() -> C.CDLL:
     return L
 
 
-EXPORTS = ("agx_create agx_create_tables agx_set_tables agx_ref_fwd_dev agx_measure_butterfly_peak agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_elementwise agx_bitrev "
+EXPORTS = ("agx_create agx_create_tables agx_set_tables agx_ref_fwd_dev agx_measure_butterfly_peak agx_destroy agx_get_psi agx_get_tables agx_ntt_fwd agx_ntt_inv agx_polymul agx_polymul_by_spectrum agx_polymul_by_spectrum_host agx_elementwise agx_bitrev "
            "agx_ntt_fwd_host agx_ntt_inv_host agx_polymul_host agx_host_alloc agx_host_free agx_fill_synthetic "
            "agx_checksum agx_ref_input agx_ref_fwd agx_ref_output agx_wait agx_error_string agx_launch_count "
            "agx_variant").split()
@@ -209,6 +211,15 @@ class Context:
         _ck(lib().agx_polymul(self._h, _dev_ptr(c), _dev_ptr(a), _dev_ptr(b), B, _stream_ptr(stream)), "agx_polymul")
         return c
 
+    def polymul_by_spectrum(self, c, a, b_hat, stream=None):
+        """c = INTT(NTT(a) .* b_hat) with b_hat = fwd(b): the product when one operand is kept in evaluation form."""
+        B = self._batch(a)
+        if self._batch(b_hat) != B or self._batch(c) != B:
+            raise ValueError("shape mismatch")
+        _ck(lib().agx_polymul_by_spectrum(self._h, _dev_ptr(c), _dev_ptr(a), _dev_ptr(b_hat), B, _stream_ptr(stream)),
+            "agx_polymul_by_spectrum")
+        return c
+
     EW = {"add": 0, "sub": 1, "mul": 2, "mac": 3}
 
     def elementwise(self, op: str, c, a, b, stream=None):
@@ -274,6 +285,11 @@ class Context:
     def polymul_host(self, c, a, b, B=None):
         _ck(lib().agx_polymul_host(self._h, self._host_ptr(c), self._host_ptr(a), self._host_ptr(b),
                                    self._host_batch(a, B)), "agx_polymul_host")
+        return c
+
+    def polymul_by_spectrum_host(self, c, a, b_hat, B=None):
+        _ck(lib().agx_polymul_by_spectrum_host(self._h, self._host_ptr(c), self._host_ptr(a), self._host_ptr(b_hat),
+                                               self._host_batch(a, B)), "agx_polymul_by_spectrum_host")
         return c
 
 

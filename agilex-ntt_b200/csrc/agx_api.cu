@@ -198,7 +198,7 @@ KParams kparams(const agx_ctx *c) {
     return KParams{c->d_tw_fwd, c->d_tw_inv, c->d_twc_fwd, c->d_twc_inv, c->d_lc, c->L, c->lc0};
 }
 
-enum Op { OP_FWD, OP_INV, OP_MUL };
+enum Op { OP_FWD, OP_INV, OP_MUL, OP_MULSPEC };   // OP_MULSPEC: b is already a spectrum (agx_polymul_by_spectrum)
 
 #ifndef AGX_TMA_STORE
 #define AGX_TMA_STORE 1
@@ -304,6 +304,14 @@ int launch_fast(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint3
     } else if (op == OP_INV) {
         AGX_INV(out);
         c->launches++;
+    } else if (op == OP_MULSPEC) {
+        // b is NTT(b) already: out = NTT(a) .* b (forward kernel with the pointwise epilogue, lazily reduced); out = INTT(out)
+        if (const CUtensorMap *tm = result_map(c, out, T, G::E, G::TPP))
+            ntt_fwd_loop_kernel<LOGN, LE, true, CL, true><<<grid, block, 0, s>>>(out, a, b, p, Tu, *tm);
+        else
+            ntt_fwd_loop_kernel<LOGN, LE, true, CL, false><<<grid, block, 0, s>>>(out, a, b, p, Tu, no_map);
+        AGX_INV(out);
+        c->launches += 2;
     } else if constexpr (LOGN <= 10) {
         // n = 1024: forward(a), forward(b), pointwise, inverse fused in one launch (its 28 KB of code fits the
         // instruction cache; at n >= 2048 the fused kernel is 57-60 KB and runs 30 % slower than the split below)
@@ -353,6 +361,27 @@ int launch_generic(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const ui
         launch_generic_ntt(c, false, out, T, s);
     } else if (op == OP_INV) {
         launch_generic_ntt(c, true, out, T, s);
+    } else if (op == OP_MULSPEC) {
+        // generic sizes, b already a spectrum: out <- NTT(a); out <- INTT(out .* b).  When out is b's buffer the spectrum
+        // is moved to a stream-ordered scratch buffer first.
+        const size_t bytes = T * c->n * 4, total = T * c->n;
+        uint32_t *tmp = nullptr;
+        cudaError_t e = cudaSuccess;
+        if (out == b) {
+            e = cudaMallocAsync(&tmp, bytes, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, b, bytes, cudaMemcpyDeviceToDevice, s);
+            b = tmp;
+        }
+        if (e == cudaSuccess && out != a) e = cudaMemcpyAsync(out, a, bytes, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) {
+            launch_generic_ntt(c, false, out, T, s);
+            pointwise_generic_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(out, b, c->d_lc, c->L, c->logn, total);
+            c->launches++;
+            launch_generic_ntt(c, true, out, T, s);
+            e = cudaGetLastError();
+        }
+        if (tmp) { const cudaError_t ef = cudaFreeAsync(tmp, s); if (e == cudaSuccess) e = ef; }
+        return (int)e;
     } else {
         // generic sizes: out <- NTT(a), tmp <- NTT(b) in a stream-ordered scratch buffer, out <- INTT(out .* tmp).
         // Every aliasing case of the fast path is served: the product commutes (out == b), squaring needs no scratch.
@@ -418,7 +447,7 @@ int launch(agx_ctx *c, Op op, uint32_t *out, const uint32_t *a, const uint32_t *
     if (T == 0) return AGX_OK;
     if (T > 0x7fffffffull) return AGX_E_INVALID;
 #if AGX_WITH_R16
-    if (c->r16) {
+    if (c->r16 && op != OP_MULSPEC) {
         int rc = 0;
         if (c->L == 1 ? launch_r16<true>(c, op, out, a, b, T, s, &rc) : launch_r16<false>(c, op, out, a, b, T, s, &rc)) return rc;
     }
@@ -533,10 +562,11 @@ int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
 int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32_t *h_out, size_t B) {
     if (!c || !c->has_parms) return AGX_E_INVALID;
     if (B == 0) return AGX_OK;
-    if (!h_a || !h_out || (op == OP_MUL && !h_b)) return AGX_E_INVALID;
+    const bool two = op == OP_MUL || op == OP_MULSPEC;
+    if (!h_a || !h_out || (two && !h_b)) return AGX_E_INVALID;
     AGX_ON_DEVICE(c);
-    const bool pin_a = is_pinned(h_a), pin_b = op != OP_MUL || is_pinned(h_b), pin_o = is_pinned(h_out);
-    int rc = pipe_prepare(c, op == OP_MUL, !(pin_a && pin_b && pin_o));
+    const bool pin_a = is_pinned(h_a), pin_b = !two || is_pinned(h_b), pin_o = is_pinned(h_out);
+    int rc = pipe_prepare(c, two, !(pin_a && pin_b && pin_o));
     if (rc) return rc;
     HostPipe &P = c->pipe;
     const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
@@ -564,7 +594,7 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
         const uint32_t *src_a = h_a + off;
         if (!pin_a) { memcpy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
         STEP(cudaMemcpyAsync(P.d_a[sl], src_a, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
-        if (op == OP_MUL) {
+        if (two) {
             const uint32_t *src_b = h_b + off;
             if (!pin_b) { memcpy(P.p_in2[sl], src_b, bytes); src_b = P.p_in2[sl]; }
             STEP(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
@@ -950,6 +980,15 @@ int agx_polymul(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db
     return launch(c, OP_MUL, dc, da, db, B, (cudaStream_t)stream);
 }
 
+int agx_polymul_by_spectrum(agx_ctx *c, uint32_t *dc, const uint32_t *da, const uint32_t *db_hat, size_t B, void *stream) {
+    int rc = check_dev_call(c, dc, B);
+    if (rc) return rc;
+    if (B && (!da || !db_hat)) return AGX_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db_hat)) & 15) return AGX_E_INVALID;
+    AGX_ON_DEVICE(c);
+    return launch(c, OP_MULSPEC, dc, da, db_hat, B, (cudaStream_t)stream);
+}
+
 int agx_elementwise(agx_ctx *c, int op, uint32_t *dc, const uint32_t *da, const uint32_t *db, size_t B, void *stream) {
     int rc = check_dev_call(c, dc, B);
     if (rc) return rc;
@@ -994,6 +1033,10 @@ int agx_ntt_inv_host(agx_ctx *c, const uint32_t *h_in, uint32_t *h_out, size_t B
 }
 int agx_polymul_host(agx_ctx *c, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b, size_t B) {
     return run_host(c, OP_MUL, h_a, h_b, h_c, B);
+}
+
+int agx_polymul_by_spectrum_host(agx_ctx *c, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b_hat, size_t B) {
+    return run_host(c, OP_MULSPEC, h_a, h_b_hat, h_c, B);
 }
 
 int agx_host_alloc(void **p, size_t bytes) {

@@ -509,6 +509,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                            "roofline": roofline_of(f"polymul<n={nn}>, {per_call} launch(es)", nn, BB, tp, 3 * nn * 4, mhz_p,
                                                    bf_per_transform=3 * (nn // 2) * logn)}
         good = good and pm_ok
+        # the same products with b kept in evaluation form (agx_polymul_by_spectrum: two launches, 5 streams of traffic):
+        # SURVEY s.8(f) rank 4; must reproduce the three-launch product bit for bit
+        want = c.checksum(out, first_index=rank * BB * nn)
+        c.fwd(b)
+        l0 = c.launch_count()
+        c.polymul_by_spectrum(out, a, b)
+        per_call_s = c.launch_count() - l0
+        ps_ok = c.checksum(out, first_index=rank * BB * nn) == want
+        ts = time_ms(lambda: c.polymul_by_spectrum(out, a, b), args.extra_iters)
+        mhz_s = last_mhz[0] or mhz_x
+        configs["cfg4_by_spectrum"] = {"workload": "configs[3] with one operand already transformed (c = INTT(NTT(a) .* b_hat)), n=2048, batch of 131,072",
+                                       "n": nn, "nlimbs": 1, "batch_per_gpu": BB, "value": world * BB / (ts * 1e-3), "unit": "products/s",
+                                       "ms": ts, "launches_per_call": per_call_s, "equals_agx_polymul": "ok" if ps_ok else "FAILED",
+                                       "roofline": roofline_of(f"polymul_by_spectrum<n={nn}>, {per_call_s} launch(es)", nn, BB, ts,
+                                                               3 * nn * 4, mhz_s, bf_per_transform=2 * (nn // 2) * logn)}
+        good = good and ps_ok
         del a, b, out
         c.close()
         for nn in (1024, 2048):

@@ -102,6 +102,15 @@ int agx_ntt_inv(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
  * transforms of that size (n >= 8192: shared-memory-resident register passes; n <= 512: the generic kernel) around a
  * pointwise launch, with a stream-ordered scratch buffer unless a == b. */
 int agx_polymul(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b, size_t B, void *stream);
+/* The product with one operand already in evaluation form -- the shape of an RLWE encryption or key switch, where the
+ * key is transformed once and multiplied many times (no reference counterpart):
+ * c = INTT(NTT(a) .* b_hat), b_hat = agx_ntt_fwd(b) (reduced, bit-reversed order as the forward transform leaves it).
+ * Two launches at n = 1024, 2048, 4096 (c = NTT(a) .* b_hat inside the forward kernel; c = INTT(c): 5 streams of HBM
+ * traffic, two transforms' worth of multiplies instead of agx_polymul's three); the generic transforms around a
+ * pointwise launch at other sizes.  c may alias a and/or b_hat (aliasing b_hat at the generic sizes costs a scratch
+ * copy).  Equals agx_polymul(c, a, b) bit for bit. */
+int agx_polymul_by_spectrum(agx_ctx *ctx, uint32_t *d_c, const uint32_t *d_a, const uint32_t *d_b_hat, size_t B,
+                            void *stream);
 
 /* ---- limb-wise element-wise arithmetic on [B][L][n] DEVICE data (the operations callers run around the transforms,
  * e.g. spectrum multiply-accumulate between agx_ntt_fwd and agx_ntt_inv; no reference
@@ -125,6 +134,7 @@ int agx_bitrev(agx_ctx *ctx, uint32_t *d_data, size_t B, void *stream);
 int agx_ntt_fwd_host(agx_ctx *ctx, const uint32_t *h_in, uint32_t *h_out, size_t B);
 int agx_ntt_inv_host(agx_ctx *ctx, const uint32_t *h_in, uint32_t *h_out, size_t B);
 int agx_polymul_host(agx_ctx *ctx, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b, size_t B);
+int agx_polymul_by_spectrum_host(agx_ctx *ctx, uint32_t *h_c, const uint32_t *h_a, const uint32_t *h_b_hat, size_t B);
 int agx_host_alloc(void **p, size_t bytes);
 int agx_host_free(void *p);
 

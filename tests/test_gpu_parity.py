@@ -338,6 +338,64 @@ def test_polymul_vs_oracle_and_schoolbook(A, torch, n):
             assert (to_np(da2).reshape(a.shape) == sq).all()
 
 
+@pytest.mark.parametrize("n", [256, 1024, 2048, 4096, 8192])
+def test_polymul_by_spectrum(A, torch, n):
+    """SURVEY s.8(f) rank 4: the product with one operand kept in evaluation form, c = INTT(NTT(a) .* b_hat), against the
+    oracle's product and exact schoolbook, bit-identical to agx_polymul, with and without the tensor store's map (odd batch),
+    every aliasing case, operands left untouched."""
+    for L in (1, 3):
+        primes = Q[:L]
+        c = ctx_for(A, n, primes)
+        P = O.Plan(n, primes)
+        B = 7
+        a, b = P.synthetic(B, seed=31), P.synthetic(B, seed=32)
+        want = P.polymul(a, b)
+        da, db = to_dev(torch, a), to_dev(torch, b)
+        bh = db.clone(); c.fwd(bh)
+        assert (to_np(bh).reshape(a.shape) == P.fwd(b.copy())).all()
+        bh_np = to_np(bh).copy()
+        dc = torch.empty_like(da)
+        c.polymul_by_spectrum(dc, da, bh)
+        got = to_np(dc).reshape(a.shape)
+        assert (got == want).all()
+        for l, q in enumerate(primes):
+            assert (got[0, l] == O.polymul_schoolbook(a[0, l], b[0, l], q)).all()
+        ref = torch.empty_like(da); c.polymul(ref, da, db)
+        assert (to_np(ref) == to_np(dc)).all()
+        assert (to_np(da).reshape(a.shape) == a).all() and (to_np(bh) == bh_np).all()
+        t = da.clone(); c.polymul_by_spectrum(t, t, bh)            # c == a
+        assert (to_np(t).reshape(a.shape) == want).all()
+        t = bh.clone(); c.polymul_by_spectrum(t, da, t)            # c == b_hat
+        assert (to_np(t).reshape(a.shape) == want).all()
+        t = da.clone(); c.polymul_by_spectrum(t, t, t)             # all three: NTT(a) .* a (a read as a spectrum)
+        ah = da.clone(); c.fwd(ah)
+        e = torch.empty_like(da); c.elementwise("mul", e, ah, da); c.inv(e)
+        assert (to_np(t) == to_np(e)).all()
+        a2 = P.synthetic(B, seed=33)                               # the spectrum is reused: a second product, other a
+        c.polymul_by_spectrum(dc, to_dev(torch, a2), bh)
+        assert (to_np(dc).reshape(a.shape) == P.polymul(a2, b)).all()
+
+
+def test_polymul_by_spectrum_host_and_errors(A, torch):
+    n = 2048
+    c = ctx_for(A, n, Q[:1])
+    P = O.Plan(n, Q[:1])
+    a, b = P.synthetic(5000, seed=41), P.synthetic(5000, seed=42)   # > one pipeline chunk (4096 polynomials)
+    bh = P.fwd(b.copy(), threads=O.max_threads())
+    out = np.empty_like(a)
+    c.polymul_by_spectrum_host(out, a, bh)
+    assert (out == P.polymul(a, b, threads=O.max_threads())).all()
+    import ctypes
+    L = A.lib()
+    d = torch.zeros(2 * n + 4, dtype=torch.int32, device="cuda")
+    ok, off = ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(d.data_ptr() + 4)
+    assert L.agx_polymul_by_spectrum(c._h, ok, ok, off, 1, None) == -1      # AGX_E_INVALID: operand not 16-byte aligned
+    assert L.agx_polymul_by_spectrum(c._h, off, ok, ok, 1, None) == -1
+    assert L.agx_polymul_by_spectrum(c._h, ok, None, ok, 1, None) == -1
+    assert L.agx_polymul_by_spectrum(c._h, ok, ok, ok, 0, None) == 0        # empty batch
+    torch.cuda.synchronize()
+
+
 def test_polymul_kat(A, torch):
     n, q = 2048, Q[0]
     c = ctx_for(A, n, [q])
