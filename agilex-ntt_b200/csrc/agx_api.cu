@@ -4,9 +4,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,6 +27,7 @@
 #include "agx_ntt_r16.cuh"
 #endif
 #include "agx_tables.h"
+#include "agx_copycrew.h"
 
 using namespace agx;
 
@@ -94,6 +99,7 @@ struct agx_ctx {
     unsigned map_next = 0;
     HostPipe pipe;
     RefState ref;
+    CopyCrew *crew_in = nullptr, *crew_out = nullptr;      // created with the first pageable call
 };
 
 namespace {
@@ -476,9 +482,9 @@ bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// Pageable callers: results are staged in pinned chunks and copied to the caller's buffer by a helper thread, so that
-// the copy-out of chunk i runs beside the staging-in of chunk i+1 on the calling thread (one thread doing both moves
-// ~4 GB/s in each direction; two move ~2x that).  Chunks are drained strictly in order.
+// Pageable callers: results are staged in pinned chunks and copied to the caller's buffer by a helper thread (with its own
+// CopyCrew), so that the copy-out of chunk i runs beside the staging-in of chunk i+1 on the calling thread.  Chunks are
+// drained strictly in order.
 class OutDrainer {
     struct Item { void *dst; const void *src; size_t bytes; cudaEvent_t ev; };
     Item items_[kSlots] = {};
@@ -487,6 +493,7 @@ class OutDrainer {
     std::atomic<bool> stop_{false};
     std::thread th_;
     int device_;
+    CopyCrew *crew_;
     void run() {
         cudaSetDevice(device_);
         for (size_t i = 0;; i++) {
@@ -497,12 +504,13 @@ class OutDrainer {
             const Item it = items_[i % kSlots];
             const cudaError_t e = cudaEventSynchronize(it.ev);
             if (e != cudaSuccess) err_.store((int)e);
+            else if (crew_) crew_->copy(it.dst, it.src, it.bytes);
             else memcpy(it.dst, it.src, it.bytes);
             drained_.store(i + 1, std::memory_order_release);
         }
     }
 public:
-    explicit OutDrainer(int device) : device_(device) {}
+    explicit OutDrainer(int device, CopyCrew *crew = nullptr) : device_(device), crew_(crew) {}
     ~OutDrainer() { finish(); }
     // before chunk i reuses its slot's staging buffers: chunk i - kSlots must have been copied out
     void wait_slot_free(size_t i) {
@@ -523,6 +531,11 @@ public:
         return err_.load();
     }
 };
+
+void ensure_crews(agx_ctx *c) {
+    if (!c->crew_in) c->crew_in = new CopyCrew();
+    if (!c->crew_out) c->crew_out = new CopyCrew();
+}
 
 int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
     HostPipe &P = c->pipe;
@@ -571,7 +584,8 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
     HostPipe &P = c->pipe;
     const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
     const size_t chunk_polys = P.cap / poly_bytes;
-    OutDrainer drain(c->device);
+    if (!(pin_a && pin_b && pin_o)) ensure_crews(c);
+    OutDrainer drain(c->device, c->crew_out);
     // One way out: whatever fails, no copy may still be touching the caller's memory when this function returns.
     auto finish = [&](int code) {
         for (int k = 0; k < kSlots; k++) {
@@ -592,11 +606,11 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
             else if (!pin_a || !pin_b) STEP(cudaEventSynchronize(P.done[sl]));
         }
         const uint32_t *src_a = h_a + off;
-        if (!pin_a) { memcpy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
+        if (!pin_a) { c->crew_in->copy(P.p_in[sl], src_a, bytes); src_a = P.p_in[sl]; }
         STEP(cudaMemcpyAsync(P.d_a[sl], src_a, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
         if (two) {
             const uint32_t *src_b = h_b + off;
-            if (!pin_b) { memcpy(P.p_in2[sl], src_b, bytes); src_b = P.p_in2[sl]; }
+            if (!pin_b) { c->crew_in->copy(P.p_in2[sl], src_b, bytes); src_b = P.p_in2[sl]; }
             STEP(cudaMemcpyAsync(P.d_b[sl], src_b, bytes, cudaMemcpyHostToDevice, P.stream[sl]));
         }
         rc = launch(c, op, P.d_a[sl], P.d_a[sl], P.d_b[sl], cnt, P.stream[sl]);
@@ -737,7 +751,8 @@ int ref_flush(agx_ctx *c) {
         R.have_stage_out = true;
     }
     const uint64_t modulus = R.mod[0];
-    OutDrainer drain(c->device);
+    if (!pin_in || !pin_out) ensure_crews(c);
+    OutDrainer drain(c->device, c->crew_out);
     // From here on copies touch the caller's buffers.  On any failure: drain every stream and the helper thread before
     // returning, so that nothing is in flight behind the caller's back; on success the round stays asynchronous and
     // agx_wait() completes it (R.busy).
@@ -776,12 +791,18 @@ int ref_flush(agx_ctx *c) {
             }
         } else {
             if (same) {
-                memcpy(R.p_in[sl], R.in + off, bytes);
-            } else {
-                for (size_t f = 0; f < cnt; f++) {
-                    memcpy(R.p_in[sl] + f * N, R.in + off + f * N, half_bytes);
-                    memcpy(R.p_in[sl] + f * N + N / 2, R.in2 + off + f * N + N / 2, half_bytes);
-                }
+                c->crew_in->copy(R.p_in[sl], R.in + off, bytes);
+            } else {                                                 // ntt.cpp:582-591: low half from in, high half from in2
+                const size_t parts = std::min<size_t>((size_t)c->crew_in->threads(), std::max<size_t>(1, bytes >> 20));
+                const size_t per = (cnt + parts - 1) / parts;
+                uint64_t *stage = R.p_in[sl];
+                const uint64_t *in = R.in, *in2 = R.in2;
+                c->crew_in->run(parts, [&](size_t part) {
+                    for (size_t f = part * per; f < std::min(cnt, (part + 1) * per); f++) {
+                        memcpy(stage + f * N, in + off + f * N, half_bytes);
+                        memcpy(stage + f * N + N / 2, in2 + off + f * N + N / 2, half_bytes);
+                    }
+                });
             }
             STEP(cudaMemcpyAsync(R.d_in[sl], R.p_in[sl], bytes, cudaMemcpyHostToDevice, st));
         }
@@ -877,6 +898,7 @@ int agx_destroy(agx_ctx *c) {
         DeviceGuard guard__(c->device);
         cudaDeviceSynchronize();
         pipe_destroy(c->pipe);
+        delete c->crew_in; delete c->crew_out;
         RefState &R = c->ref;
         for (int i = 0; i < kSlots; i++) {
             cudaFree(R.d_in[i]); cudaFree(R.d_out[i]);

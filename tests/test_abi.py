@@ -80,3 +80,13 @@ def test_compat_driver_builds():
     tools = A.build.build_tools()
     assert os.path.exists(tools["main_compat"])
     assert os.path.exists(tools["c_example"])      # include/agxntt.h is valid, warning-free C99 (-Werror -pedantic)
+
+
+def test_copycrew_stress(tmp_path):
+    """Host logic of the pageable-caller pipelines (csrc/agx_copycrew.h: helper threads that split a staging copy): every
+    byte of copies of awkward sizes, two crews driven by two threads at once, 1-6 threads each, and the thread-count knob."""
+    exe = str(tmp_path / "copycrew_stress")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "agilex-ntt_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "native", "copycrew_stress.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "copycrew ok" in r.stdout, r.stdout + r.stderr
