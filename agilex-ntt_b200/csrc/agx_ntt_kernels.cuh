@@ -974,9 +974,32 @@ __global__ void __launch_bounds__(256) bitrev_rows_kernel(uint32_t *__restrict__
 #ifndef AGX_U64_VECTW
 #define AGX_U64_VECTW 1
 #endif
+// AGX_U64_BORROW: the x-correction (ntt.cpp:331-332) decided by the borrow of the 64-bit subtraction it needs anyway
+// instead of a separate 64-bit compare: two ISETP less per butterfly, and fewer of the remaining adds placed on the multiply
+// pipe by ptxas -- the isolated butterfly stream goes from 3.00-3.05 to 3.36-3.38 butterflies/clk/SM, the frame kernel gains
+// 4 % (experiments/u64_bfly_variants2.cu, profiles/r02_u64_borrow_ab.txt).
+#ifndef AGX_U64_BORROW
+#define AGX_U64_BORROW 1
+#endif
+__device__ __forceinline__ uint64_t ref_csub_u64(uint64_t x, uint64_t m) {
+#if AGX_U64_BORROW
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    uint32_t d0, d1, b;
+    asm("{\n\t"
+        "sub.cc.u32 %0, %3, %5;\n\t"
+        "subc.cc.u32 %1, %4, %6;\n\t"
+        "subc.u32 %2, 0, 0;\n\t"
+        "}" : "=r"(d0), "=r"(d1), "=r"(b) : "r"(x0), "r"(x1), "r"((uint32_t)m), "r"((uint32_t)(m >> 32)));
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(b ? x0 : d0), "r"(b ? x1 : d1));
+    return r;
+#else
+    return x >= m ? x - m : x;
+#endif
+}
+
 __device__ __forceinline__ void ref_bfly_u64(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twice) {
-    uint64_t tx = x;
-    if (tx >= twice) tx -= twice;                 // ntt.cpp:331-332
+    const uint64_t tx = ref_csub_u64(x, twice);   // ntt.cpp:331-332
     const uint64_t c1 = __umul64hi(y, Wp);        // ntt.cpp:344-358
 #if AGX_U64_NEGQ
     uint64_t negq;                                // -q through an opaque (pure, hence hoisted and shared) instruction:
@@ -1089,10 +1112,7 @@ __global__ void __launch_bounds__(128) ref_u64_last_pass_kernel(uint64_t *data, 
     const uint64_t twice = q << 1;
 #pragma unroll
     for (int k = 0; k < E; k++) {                             // ntt.cpp:377-393
-        uint64_t v = x[k];
-        if (v >= twice) v -= twice;
-        if (v >= q) v -= q;
-        x[k] = v;
+        x[k] = ref_csub_u64(ref_csub_u64(x[k], twice), q);
     }
     __syncwarp();
 #pragma unroll
@@ -1214,10 +1234,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
         ref_pass16_u64<VEC, 0>(x, roots, precons, s_done + split, vt + (half_id << s_done), q, twice);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            uint64_t v = x[k];
-            if (v >= twice) v -= twice;
-            if (v >= q) v -= q;
-            s[k] = v;
+            s[k] = ref_csub_u64(ref_csub_u64(x[k], twice), q);
         }
     }
     __syncthreads();
