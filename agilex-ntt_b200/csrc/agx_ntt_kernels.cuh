@@ -977,7 +977,7 @@ __global__ void __launch_bounds__(256) bitrev_rows_kernel(uint32_t *__restrict__
 // AGX_U64_BORROW: the x-correction (ntt.cpp:331-332) decided by the borrow of the 64-bit subtraction it needs anyway
 // instead of a separate 64-bit compare: two ISETP less per butterfly, and fewer of the remaining adds placed on the multiply
 // pipe by ptxas -- the isolated butterfly stream goes from 3.00-3.05 to 3.36-3.38 butterflies/clk/SM, the frame kernel gains
-// 4 % (experiments/u64_bfly_variants2.cu, profiles/r02_u64_borrow_ab.txt).
+// 4 % (profiles/r02_u64_borrow_ab.txt).
 #ifndef AGX_U64_BORROW
 #define AGX_U64_BORROW 1
 #endif
