@@ -492,6 +492,7 @@ class OutDrainer {
     std::atomic<int> err_{0};
     std::atomic<bool> stop_{false};
     std::thread th_;
+    bool inline_ = false;
     int device_;
     CopyCrew *crew_;
     void run() {
@@ -518,7 +519,18 @@ public:
         while (drained_.load(std::memory_order_acquire) < i - kSlots + 1) std::this_thread::yield();
     }
     void submit(size_t i, void *dst, const void *src, size_t bytes, cudaEvent_t ev) {
-        if (!th_.joinable()) th_ = std::thread(&OutDrainer::run, this);
+        if (!th_.joinable() && !inline_) {
+            try { th_ = std::thread(&OutDrainer::run, this); } catch (...) { inline_ = true; }   // nothing throws across the C ABI
+        }
+        if (inline_) {                                   // no helper thread to be had: drain on the calling thread
+            const cudaError_t e = cudaEventSynchronize(ev);
+            if (e != cudaSuccess) err_.store((int)e);
+            else if (crew_) crew_->copy(dst, src, bytes);
+            else memcpy(dst, src, bytes);
+            issued_.store(i + 1, std::memory_order_release);
+            drained_.store(i + 1, std::memory_order_release);
+            return;
+        }
         items_[i % kSlots] = Item{dst, src, bytes, ev};
         issued_.store(i + 1, std::memory_order_release);
     }
@@ -532,9 +544,14 @@ public:
     }
 };
 
-void ensure_crews(agx_ctx *c) {
-    if (!c->crew_in) c->crew_in = new CopyCrew();
-    if (!c->crew_out) c->crew_out = new CopyCrew();
+int ensure_crews(agx_ctx *c) {
+    try {                                              // thread creation can fail; nothing may throw across the C ABI
+        if (!c->crew_in) c->crew_in = new CopyCrew();
+        if (!c->crew_out) c->crew_out = new CopyCrew();
+    } catch (...) {
+        return AGX_E_NOMEM;
+    }
+    return AGX_OK;
 }
 
 int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
@@ -584,7 +601,7 @@ int run_host(agx_ctx *c, Op op, const uint32_t *h_a, const uint32_t *h_b, uint32
     HostPipe &P = c->pipe;
     const size_t poly_words = (size_t)c->L * c->n, poly_bytes = poly_words * 4;
     const size_t chunk_polys = P.cap / poly_bytes;
-    if (!(pin_a && pin_b && pin_o)) ensure_crews(c);
+    if (!(pin_a && pin_b && pin_o) && (rc = ensure_crews(c)) != AGX_OK) return rc;
     OutDrainer drain(c->device, c->crew_out);
     // One way out: whatever fails, no copy may still be touching the caller's memory when this function returns.
     auto finish = [&](int code) {
@@ -751,7 +768,7 @@ int ref_flush(agx_ctx *c) {
         R.have_stage_out = true;
     }
     const uint64_t modulus = R.mod[0];
-    if (!pin_in || !pin_out) ensure_crews(c);
+    if (!pin_in || !pin_out) { const int rc = ensure_crews(c); if (rc) return rc; }
     OutDrainer drain(c->device, c->crew_out);
     // From here on copies touch the caller's buffers.  On any failure: drain every stream and the helper thread before
     // returning, so that nothing is in flight behind the caller's back; on success the round stays asynchronous and
