@@ -51,7 +51,7 @@ struct HostPipe {
     bool have_b = false, have_stage = false;
 };
 
-constexpr size_t kRefChunkBytes = 16u << 20;       // frame data per slot of the reference-shaped pipeline
+constexpr size_t kRefChunkBytes = 16u << 20;       // frame data per slot of the reference-shaped pipeline when the SM count is unknown
 
 struct RefState {
     bool have_in = false, have_fwd = false, have_out = false, busy = false;
@@ -736,7 +736,18 @@ int ref_flush(agx_ctx *c) {
         CK(cudaEventCreateWithFlags(&R.tables, cudaEventDisableTiming));
     }
     const size_t N = R.N, frame_bytes = N * 8, half_bytes = N * 4;
-    size_t chunk_frames = kRefChunkBytes / frame_bytes;
+    // Chunk = whole waves of frame CTAs (a wave is SMs x 128 KiB of frames at every N the frame kernel serves: N/32 threads
+    // per CTA, 512 per SM; half as many frames at N = 32768): a chunk's kernel takes a wave's time whether the wave is full or
+    // not, and that time is added to the copy engines' period (profiles/pipeline_timeline.py).  Two waves for rounds of half a
+    // GiB and more, where fill and drain matter less: 43.0 -> 44.7 GB/s each way on 1 GiB rounds against the former 16 MiB
+    // (profiles/r02_u64_chunk_sweep.jsonl).
+    size_t ref_chunk_bytes = c->sms > 0 ? (size_t)c->sms << 17 : kRefChunkBytes;
+    if ((size_t)R.frames * frame_bytes >= ((size_t)512 << 20)) ref_chunk_bytes *= 2;
+    if (const char *e = getenv("AGX_REF_CHUNK_KB")) {               // tuning knob, like AGX_HOST_CHUNK_MB
+        const long kb = atol(e);
+        if (kb >= 64 && kb <= (1 << 20)) ref_chunk_bytes = (size_t)kb << 10;
+    }
+    size_t chunk_frames = ref_chunk_bytes / frame_bytes;
     if (chunk_frames == 0) chunk_frames = 1;
     if (chunk_frames > R.frames) chunk_frames = R.frames;
     const size_t chunk_bytes = chunk_frames * frame_bytes;

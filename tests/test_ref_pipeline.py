@@ -188,9 +188,11 @@ v_holder = []
 
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("same", [True, False])
-def test_chunked_pipeline_many_frames(A, pinned, same):
-    """More frames than one pipeline chunk holds (3 slots x 16 MiB): H2D / kernel / D2H overlap across slots; the high
-    halves come from in2 (ntt.cpp:582-591), by pitched copies when the caller's buffers are page-locked."""
+def test_chunked_pipeline_many_frames(A, pinned, same, monkeypatch):
+    """More frames than one pipeline chunk holds (3 slots; chunk pinned to 16 MiB here, the library's own choice is whole
+    waves of frame CTAs): H2D / kernel / D2H overlap across slots; the high halves come from in2 (ntt.cpp:582-591), by
+    pitched copies when the caller's buffers are page-locked."""
+    monkeypatch.setenv("AGX_REF_CHUNK_KB", "16384")
     N, q = 8192, O.SEAL_PRIMES_30[2]
     frames = 4 * (16 << 20) // (N * 8) + 5          # 4 full chunks and a ragged one
     tw, pre = O.tables_u64(N, q)
@@ -214,6 +216,21 @@ def test_chunked_pipeline_many_frames(A, pinned, same):
         assert launches == 5
     assert (out == want).all()
     v_holder.clear()
+
+
+def test_default_chunks_are_whole_waves(A):
+    """The pipeline's own chunking: SMs x 128 KiB of frames per chunk (one wave of frame CTAs), ragged last chunk, results
+    as the restatement's."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    N, q = 16384, O.U64_PRIMES[60]
+    frames = 2 * sms + 9
+    tw, pre = O.tables_u64(N, q)
+    rng = np.random.default_rng(11)
+    x = rng.integers(0, 4 * q, size=N * frames, dtype=np.uint64)
+    out, launches = run_pipeline(A, x, x, q, tw, pre, frames)
+    assert launches == 3
+    assert (out == O.batch_ref_fwd_u64(N, x.copy(), q, tw, pre, threads=O.max_threads())).all()
 
 
 @pytest.mark.parametrize("N,bits", [(1024, 60), (8192, 50), (16384, 60), (32768, 50), (64, 60)])
