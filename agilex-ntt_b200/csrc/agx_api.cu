@@ -40,7 +40,7 @@ using namespace agx;
 namespace {
 
 constexpr int kSlots = 3;                          // host pipeline depth (H2D / kernel / D2H in flight)
-constexpr size_t kChunkBytes = 32u << 20;          // per-slot chunk of the host pipeline
+constexpr size_t kChunkBytes = 32u << 20;          // per-slot chunk of the host pipeline when the SM count is unknown
 
 struct HostPipe {
     cudaStream_t stream[kSlots] = {};
@@ -562,7 +562,10 @@ int pipe_prepare(agx_ctx *c, bool need_b, bool need_stage) {
             CK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
         }
         const size_t poly_bytes = (size_t)c->L * c->n * 4;
-        size_t chunk_bytes = kChunkBytes;
+        // two waves of transform CTAs per chunk (a wave is SMs x 128 KiB of rows at n = 4096 and 2048): a chunk's kernel takes
+        // whole waves' time, and that time is added to the copy engines' period (profiles/pipeline_timeline.py); 37 MiB on a
+        // B200 against the former 32: 1.408-1.412 -> 1.416-1.419 M pairs/s end to end in one call
+        size_t chunk_bytes = c->sms > 0 ? (size_t)c->sms << 18 : kChunkBytes;
         if (const char *e = getenv("AGX_HOST_CHUNK_MB")) {            // tuning knob for the host pipeline
             const long mb = atol(e);
             if (mb >= 1 && mb <= 1024) chunk_bytes = (size_t)mb << 20;

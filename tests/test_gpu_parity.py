@@ -431,7 +431,7 @@ def test_host_entry_points(A, torch, pinned):
     n = 4096
     c = ctx_for(A, n, Q)
     P = O.Plan(n, Q)
-    B = 1500                      # > one 32 MiB chunk of the pipeline (=682 polys at L=3): exercises slot reuse
+    B = 2500                      # four chunks of the pipeline (37 MiB = 789 polys at L=3): exercises slot reuse
     x = P.synthetic(B, seed=3)
     want = P.fwd(x.copy(), threads=O.max_threads())
     if pinned:
