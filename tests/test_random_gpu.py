@@ -87,7 +87,13 @@ def test_random_parameters_against_the_oracle(A, torch, logn, primes, B, root_pi
         P = O.Plan(n, primes)
         dc = torch.empty_like(d)
         c.polymul(dc, dev(x), dev(z))
-        assert (back(dc) == P.polymul(x.copy(), z.copy())).all(), "product"
+        prod = P.polymul(x.copy(), z.copy())
+        assert (back(dc) == prod).all(), "product"
+        zh = dev(z)                                        # the same product with z kept in evaluation form, in place on x
+        c.fwd(zh)
+        dx = dev(x)
+        c.polymul_by_spectrum(dx, dx, zh)
+        assert (back(dx) == prod).all(), "product by spectrum"
     c.close()
 
 
