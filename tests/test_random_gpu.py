@@ -148,3 +148,59 @@ def test_random_u64_frames_against_the_restatement(A, torch, logn, frames, kind,
     p.wait()
     assert (out == want).all(), "host pipeline"
     p.close()
+
+
+def _host_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(count):
+        logn = int(rng.choice([10, 11, 12, 12, 13]))
+        L = int(rng.integers(1, 4))
+        row_bytes = (4 << logn) * L
+        B = int(rng.integers(1, max(2, (110 << 20) // row_bytes)))       # up to ~110 MiB: one to three pipeline chunks, ragged
+        out.append(pytest.param(logn, L, B, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)),
+                                int(rng.integers(1, 1 << 30)), id=f"h{i}-n{1 << logn}-L{L}-B{B}"))
+    return out
+
+
+@pytest.mark.parametrize("logn,L,B,pin_in,pin_out,in_place,seed",
+                         _host_cases(int(os.environ.get("AGX_RANDOM_CASES_HOST", "10")), int(os.environ.get("AGX_RANDOM_SEED", "20261018")) + 2))
+def test_random_host_pipelines(A, torch, logn, L, B, pin_in, pin_out, in_place, seed):
+    """Host-pointer entry points on random shapes: pageable and page-locked buffers in every combination (the pageable side
+    goes through the staging copies of csrc/agx_copycrew.h), in place or not, batches that end inside a pipeline chunk --
+    forward against the oracle, inverse back to the input, and the two products on a prefix."""
+    n = 1 << logn
+    primes = list(PRIMES)[:L]
+    P = O.Plan(n, primes)
+    c = A.Context(n, primes)
+    x = P.synthetic(B, seed=seed)
+    want = P.fwd(x.copy(), threads=O.max_threads())
+
+    def buf(a, pinned):
+        if not pinned:
+            return a.copy(), (lambda b: b)
+        t = torch.from_numpy(a.view(np.int32).copy()).pin_memory()
+        return t, (lambda b: b.numpy().view(np.uint32).reshape(a.shape))
+
+    src, view_src = buf(x, pin_in)
+    if in_place:
+        dst, view_dst = src, view_src
+    else:
+        dst, view_dst = buf(np.zeros_like(x), pin_out)
+    c.fwd_host(src, dst)
+    assert (view_dst(dst) == want).all(), "fwd_host"
+    c.inv_host(dst)
+    assert (view_dst(dst) == x).all(), "inv_host"
+    m = min(B, 64)                                                       # products on a prefix (the CPU product is the slow side)
+    a, b = x[:m].copy(), P.synthetic(m, seed=seed + 1)
+    prod = P.polymul(a.copy(), b.copy(), threads=O.max_threads())
+    oa, va = buf(a, pin_in)
+    ob, vb = buf(b, pin_out)
+    oc, vc = buf(np.zeros_like(a), pin_out)
+    c.polymul_host(oc, oa, ob)
+    assert (vc(oc) == prod).all(), "polymul_host"
+    bh = P.fwd(b.copy())
+    obh, _ = buf(bh, pin_in)
+    c.polymul_by_spectrum_host(oa, oa, obh)                              # in place on a
+    assert (va(oa) == prod).all(), "polymul_by_spectrum_host"
+    c.close()
