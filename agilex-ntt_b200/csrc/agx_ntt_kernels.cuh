@@ -1163,8 +1163,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
     constexpr bool VEC = AGX_U64_VECTW >= 2 || (AGX_U64_VECTW == 1 && NT >= 512);   // 16-byte twiddle pairs
     const uint32_t tid = threadIdx.x;
     const uint32_t frame = split ? blockIdx.x >> 1 : blockIdx.x, half_id = split ? blockIdx.x & 1u : 0u;
-    const uint32_t lg = logn - split;                              // log2 of the coefficients this CTA owns
-    const uint32_t M = 1u << lg, vthreads = M >> 4;
+    // log2 of the coefficients this CTA owns: always log2(NT) + 5 (a CTA is N/32 threads, agx_api.cu ref_launch), so it is a
+    // compile-time constant and with it every pass's bit position, stride and stage count: shared-memory accesses become
+    // base + immediate and the pass loop unrolls into exactly the passes this size runs
+    constexpr uint32_t lg = (NT == 512 ? 14u : NT == 256 ? 13u : NT == 128 ? 12u : NT == 64 ? 11u : 10u);
+    constexpr uint32_t M = 1u << lg, vthreads = M >> 4;
+    if (logn - split != lg) return;                                // launch contract (never taken)
     const uint64_t twice = q << 1;
     const size_t fbase = (size_t)frame << logn;
     const uint64_t *lo_src = in + fbase, *hi_src = in2 + fbase;    // low / high half of the frame (ntt.cpp:587-589)
@@ -1172,7 +1176,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
 
     // ---- pass 0: stages (split ..) on index bits [lg-4, lg), coefficients straight from global memory
     {
-        const uint32_t lo = lg - 4;
+        constexpr uint32_t lo = lg - 4;
+#pragma unroll 1
         for (uint32_t vt = tid; vt < vthreads; vt += NT) {
             if (split) {
                 // stage 0 of the 32768-point frame, this CTA keeping only its half (ntt.cpp:331-369 with roots[1])
@@ -1195,7 +1200,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
             // (roots index = 2^(s+split) + (half_id << s) + local group)
             ref_pass16_u64<VEC, 0>(x, roots, precons, split, half_id, q, twice);
             uint64_t *s = img + vt + (vt >> 4);
-            const uint32_t stride = (1u << lo) + (1u << (lo - 4));
+            constexpr uint32_t stride = (1u << lo) + (1u << (lo - 4));
 #pragma unroll
             for (int k = 0; k < 16; k++) s[k * stride] = x[k];
         }
@@ -1203,10 +1208,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
     __syncthreads();
     // ---- middle passes: index bits from lg-5 down to 4, four at a time (the last one may cover fewer)
     uint32_t s_done = 4;                                           // stages of the sub-transform finished so far
+#pragma unroll
     for (int rem = (int)lg - 8; rem > 0; rem -= 4) {
         const uint32_t lo = rem >= 4 ? (uint32_t)rem : 4u;
         const uint32_t jfirst = rem >= 4 ? 0u : (uint32_t)(4 - rem);
         const uint32_t stride = (1u << lo) + (1u << (lo - 4));
+#pragma unroll 1
         for (uint32_t vt = tid; vt < vthreads; vt += NT) {
             const uint32_t t_lo = vt & ((1u << lo) - 1), t_hi = vt >> lo;
             const uint32_t idx0 = (t_hi << (lo + 4)) + t_lo;
@@ -1227,6 +1234,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) ref_u64_frame_kernel(const uint6
         __syncthreads();
     }
     // ---- final pass: bits 3..0 (16 consecutive coefficients), reduction to [0,q) (ntt.cpp:377-393)
+#pragma unroll 1
     for (uint32_t vt = tid; vt < vthreads; vt += NT) {
         uint64_t *s = img + vt * 17;
 #pragma unroll
