@@ -351,8 +351,13 @@ void launch_generic_ntt(agx_ctx *c, bool inverse, uint32_t *d, size_t T, cudaStr
     if (c->big) {
         const size_t smem = ((size_t)c->n + c->n / 32) * 4;
         const unsigned threads = c->logn <= 14 ? 512 : 1024;   // two CTAs per SM cover each other's barriers where they fit
-        if (inverse) ntt_big_kernel<true><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
-        else ntt_big_kernel<false><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L, c->logn);
+#define AGX_BIG(LOGN)                                                                                 \
+    do {                                                                                              \
+        if (inverse) ntt_big_kernel<true, LOGN><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L);  \
+        else ntt_big_kernel<false, LOGN><<<(unsigned)T, threads, smem, s>>>(d, tw, c->d_lc, c->L);         \
+    } while (0)
+        if (c->logn == 13) AGX_BIG(13); else if (c->logn == 14) AGX_BIG(14); else AGX_BIG(15);
+#undef AGX_BIG
     } else {
         const size_t smem = (size_t)c->n * 4;
         const unsigned threads = c->n / 2 < 256 ? (c->n / 2 < 32 ? 32 : c->n / 2) : 256;
@@ -884,8 +889,11 @@ int agx_create_tables(agx_ctx **out, const agx_parms *parms, const uint32_t *psi
     {
         cudaError_t e = cudaFuncSetAttribute(ntt_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4);
+#define AGX_BIG_SMEM(LOGN)                                                                                                              \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<false, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_big_kernel<true, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024 * 4);
+        AGX_BIG_SMEM(13) AGX_BIG_SMEM(14) AGX_BIG_SMEM(15)
+#undef AGX_BIG_SMEM
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_fwd_u64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
         const int frame_smem = 17 * 1024 * 8;                          // N = 16384 image: 136 KB
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ref_u64_frame_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);

@@ -772,18 +772,23 @@ __device__ __forceinline__ void big_pass16_jf(uint32_t (&x)[16], const uint2 *__
     else big_pass16<INVERSE, 3>(x, tw, sf, t_hi, c);
 }
 
-template <bool INVERSE>
+// LOGN is a template parameter so that every pass's bit position, stride and stage count is a compile-time constant (image
+// accesses are base + immediate, the pass loop unrolls into exactly the passes a size runs), as in ref_u64_frame_kernel.
+template <bool INVERSE, int LOGN>
 __global__ void __launch_bounds__(1024, 1) ntt_big_kernel(uint32_t *data, const uint2 *__restrict__ tw_nat,
-                                                           const LimbConst *__restrict__ lc, uint32_t L, uint32_t logn) {
+                                                           const LimbConst *__restrict__ lc, uint32_t L) {
     extern __shared__ uint32_t bimg[];
-    const uint32_t n = 1u << logn, vthreads = n >> 4, tid = threadIdx.x, NT = blockDim.x;
+    constexpr uint32_t logn = LOGN;
+    constexpr uint32_t n = 1u << logn, vthreads = n >> 4;
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
     const uint32_t poly = blockIdx.x, limb = poly % L;
     const LimbConst c = lc[limb];
     const uint2 *tw = tw_nat + (size_t)limb * n;
     uint32_t *g = data + (size_t)poly * n;
-    const int np = 2 + (int)((logn - 8 + 3) / 4);              // pass 0, the passes on the bits between, the final pass
+    constexpr int np = 2 + (int)((logn - 8 + 3) / 4);          // pass 0, the passes on the bits between, the final pass
     uint32_t x[16];
 
+#pragma unroll
     for (int pp = 0; pp < np; pp++) {
         const int p = INVERSE ? np - 1 - pp : pp;
         uint32_t lo, jf, sf;
@@ -800,6 +805,7 @@ __global__ void __launch_bounds__(1024, 1) ntt_big_kernel(uint32_t *data, const 
         // uniform or compile-time terms: lo >= 5: k << lo is a multiple of 32, stride = 2^lo + 2^(lo-5), fix = 0;
         // lo == 4 (idx0 % 256 < 16): stride = 16, fix = k >> 1;  lo == 0 (idx0 % 16 == 0): stride = 1, fix = 0.
         const uint32_t stride = lo >= 5 ? (1u << lo) + (1u << (lo - 5)) : (1u << lo);
+#pragma unroll 1
         for (uint32_t vt = tid; vt < vthreads; vt += NT) {
             const uint32_t t_lo = vt & ((1u << lo) - 1), t_hi = vt >> lo;
             const uint32_t idx0 = (t_hi << (lo + 4)) + t_lo;
